@@ -1,0 +1,570 @@
+// libcloudsc2_b200.so -- CUDA kernels (sm_100a) and the C ABI declared in include/cloudsc2_b200.h.
+//
+// Kernel shapes (see DESIGN.md for the roofline of each):
+//   * pointwise kernels (saturation, state_increment, perturbed_state): one element per thread
+//     per field, grid (ceil(ncol/256), levels): pure HBM streaming.
+//   * column kernels (NL, TL, AD forward, AD backward): one thread per column, 128-thread CTAs,
+//     sequential walk over the 137 levels with the flux / overlap carries in registers; a warp
+//     reads/writes 32 consecutive columns of one level per request (256 B in fp64).
+//   * reductions (Taylor sums, symmetry inner products): fp64 accumulation, warp shuffles,
+//     deterministic two-stage block reduction.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "cs2_columns.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return CS2_OK;
+  return fail(CS2_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int check_dims(const cs2_dims* d) {
+  if (!d) return fail(CS2_ERR_NULL_POINTER, "dims is NULL");
+  if (d->dtype != CS2_F64 && d->dtype != CS2_F32) return fail(CS2_ERR_BAD_DIMS, "dtype must be CS2_F64 or CS2_F32");
+  if (d->ncol < 0 || d->nlev < 1 || d->nlev > 4096) return fail(CS2_ERR_BAD_DIMS, "ncol < 0 or nlev outside [1, 4096]");
+  if (d->ncol_stride < d->ncol) return fail(CS2_ERR_BAD_DIMS, "ncol_stride < ncol");
+  if (d->ncol_stride % 32 != 0) return fail(CS2_ERR_MISALIGNED, "ncol_stride must be a multiple of 32 elements");
+  return CS2_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_ptrs(const void* const* ptrs, int n, const char* what) {
+  for (int i = 0; i < n; ++i) {
+    if (!ptrs[i]) return fail(CS2_ERR_NULL_POINTER, std::string(what) + ": field pointer " + std::to_string(i) + " is NULL");
+    if (!aligned16(ptrs[i]))
+      return fail(CS2_ERR_MISALIGNED, std::string(what) + ": field pointer " + std::to_string(i) + " is not 16-byte aligned");
+  }
+  return CS2_OK;
+}
+
+int check_nl_fields(const cs2_nl_fields* f, const char* what) {
+  if (!f) return fail(CS2_ERR_NULL_POINTER, std::string(what) + " is NULL");
+  static_assert(sizeof(cs2_nl_fields) == 26 * sizeof(void*), "cs2_nl_fields layout");
+  return check_ptrs(reinterpret_cast<const void* const*>(f), 26, what);
+}
+
+constexpr int kColumnBlock = 128;
+constexpr int kPointBlock = 256;
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(kPointBlock)
+saturation_kernel(const __grid_constant__ cs2::DevParams<R> p, int lphylin, const R* __restrict__ ap,
+                  const R* __restrict__ t, R* __restrict__ qsat, int64_t ncol, int64_t S) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const int64_t off = int64_t(blockIdx.y) * S + i;
+  qsat[off] = cs2::saturation_point<R>(p, lphylin != 0, ap[off], t[off]);
+}
+
+template <class R>
+struct StatePtrs {
+  const R* in[CS2_NSTATE];
+  const R* in_i[CS2_NSTATE];
+  R* out[CS2_NSTATE];
+};
+
+template <class R>
+__global__ void __launch_bounds__(kPointBlock)
+state_increment_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int ignore_supsat, int64_t ncol, int64_t S) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const int64_t off = int64_t(blockIdx.y) * S + i;
+  R v[CS2_NSTATE];
+#pragma unroll
+  for (int n = 0; n < CS2_NSTATE; ++n) v[n] = f.in[n][off];
+#pragma unroll
+  for (int n = 0; n < CS2_NSTATE; ++n) f.out[n][off] = fac * v[n];
+  if (ignore_supsat) f.out[CS2_NSTATE - 1][off] = R(0);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kPointBlock)
+perturbed_state_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int64_t ncol, int64_t S) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const int64_t off = int64_t(blockIdx.y) * S + i;
+  R v[CS2_NSTATE], w[CS2_NSTATE];
+#pragma unroll
+  for (int n = 0; n < CS2_NSTATE; ++n) {
+    v[n] = f.in[n][off];
+    w[n] = f.in_i[n][off];
+  }
+#pragma unroll
+  for (int n = 0; n < CS2_NSTATE; ++n) f.out[n][off] = v[n] + fac * w[n];
+}
+
+template <class R, class C>
+__global__ void __launch_bounds__(kColumnBlock)
+nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+          const __grid_constant__ cs2::NLFields<R> f, int64_t ncol, int64_t S, int nlev, int ad_ref,
+          int32_t* jsel_out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::column_nl<R, C>(p, tab, f, S, nlev, i, ad_ref != 0, jsel_out);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kColumnBlock)
+tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+          const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g, int64_t ncol,
+          int64_t S, int nlev) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::column_tl<R>(p, tab, f, g, S, nlev, i);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kColumnBlock)
+ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+              const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADSeeds<R> s,
+              const __grid_constant__ cs2::ADOut<R> a, const int32_t* __restrict__ jsel, int64_t ncol, int64_t S,
+              int nlev) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::column_ad_bwd<R>(p, tab, f, s, a, jsel, S, nlev, i);
+}
+
+// ---- reductions -----------------------------------------------------------------------
+constexpr int kMaxRedFields = 16;
+struct RedPtrs {
+  const void* a[kMaxRedFields];
+  const void* b[kMaxRedFields];
+  const void* c[kMaxRedFields];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grid (nblk, nfields): partial[f][blk] = { sum(a - b), sum(c) } over this block's elements
+template <class R>
+__global__ void __launch_bounds__(256)
+taylor_partial_kernel(const __grid_constant__ RedPtrs f, int64_t ncol, int64_t S, int nlevp1, double2* partial) {
+  const int fld = blockIdx.y;
+  const R* a = static_cast<const R*>(f.a[fld]);
+  const R* b = static_cast<const R*>(f.b[fld]);
+  const R* c = static_cast<const R*>(f.c[fld]);
+  double s0 = 0.0, s1 = 0.0;
+  const int64_t n = ncol * nlevp1;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t k = e / ncol, i = e - k * ncol;
+    const int64_t off = k * S + i;
+    if (a) s0 += double(a[off]) - (b ? double(b[off]) : 0.0);
+    if (c) s1 += double(c[off]);
+  }
+  __shared__ double sh0[8], sh1[8];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh0[w] = s0; sh1[w] = s1; }
+  __syncthreads();
+  if (w == 0) {
+    s0 = lane < 8 ? sh0[lane] : 0.0;
+    s1 = lane < 8 ? sh1[lane] : 0.0;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) partial[int64_t(fld) * gridDim.x + blockIdx.x] = make_double2(s0, s1);
+  }
+}
+
+// one warp per field: sums[2f], sums[2f+1] += fixed-order sum of the partials
+__global__ void taylor_final_kernel(const double2* partial, int nblk, double* sums) {
+  const int fld = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 32) {
+    const double2 v = partial[int64_t(fld) * nblk + b];
+    s0 += v.x;
+    s1 += v.y;
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (threadIdx.x == 0) {
+    sums[2 * fld] += s0;
+    sums[2 * fld + 1] += s1;
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kColumnBlock)
+symmetry_norm_kernel(const __grid_constant__ RedPtrs f, int nfields, int64_t ncol, int64_t S, int nlevp1,
+                     double* norm) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  double acc = 0.0;
+  for (int n = 0; n < nfields; ++n) {
+    const R* a = static_cast<const R*>(f.a[n]);
+    const R* b = static_cast<const R*>(f.b[n]);
+    double s = 0.0;
+    for (int k = 0; k < nlevp1; ++k) s += double(a[int64_t(k) * S + i]) * double(b[int64_t(k) * S + i]);
+    acc += s;
+  }
+  norm[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------
+template <class R>
+void build_tables(const cs2_params& P, int nlev, const R* eta, void* out) {
+  // window levels: 0.1 < eta[k] < 0.4 for k in [0, nlev-2]  (nonlinear/_stencils/cloudsc2.py:109-110)
+  int32_t nw = 0;
+  for (int k = 0; k + 1 < nlev; ++k)
+    if (eta[k] > R(0.1) && eta[k] < R(0.4)) ++nw;
+  char* b = static_cast<char*>(out);
+  reinterpret_cast<int32_t*>(b)[0] = nlev;
+  reinterpret_cast<int32_t*>(b)[1] = nw;
+  reinterpret_cast<int32_t*>(b)[2] = 0;
+  reinterpret_cast<int32_t*>(b)[3] = 0;
+  size_t off = 16;
+  R* scalm = reinterpret_cast<R*>(b + off);
+  off += cs2::tables_align16(size_t(nlev) * sizeof(R));
+  R* crh2 = reinterpret_cast<R*>(b + off);
+  off += cs2::tables_align16(size_t(nlev) * size_t(nw + 1) * sizeof(R));
+  int32_t* wlev = reinterpret_cast<int32_t*>(b + off);
+  {
+    int j = 0;
+    for (int k = 0; k + 1 < nlev; ++k)
+      if (eta[k] > R(0.1) && eta[k] < R(0.4)) wlev[j++] = k;
+  }
+  for (int k = 0; k < nlev; ++k) {
+    // :127  scalm = ZSCAL * max(eta - 0.2, ZEPS1) ** 0.2
+    const R x = eta[k] - R(0.2);
+    const R m = x > R(P.ZEPS1) ? x : R(P.ZEPS1);
+    scalm[k] = R(P.ZSCAL) * R(std::pow(m, R(0.2)));
+    for (int j = 0; j <= nw; ++j) {
+      // :165-186 for trpaus = candidate j
+      const R trp = (j == 0) ? R(0.1) : eta[wlev[j - 1]];
+      const R e = eta[k];
+      const R u = (trp - R(0.25)) / R(0.15);
+      const R mn = (trp - R(0.25)) < R(0) ? (trp - R(0.25)) : R(0);
+      const R rh2 = R(0.35) + R(0.14) * (u * u) + R(0.04) * mn / R(0.15);
+      const R rh1 = R(1), rh3 = R(1);
+      R c;
+      if (e < trp) {
+        c = rh3;
+      } else {
+        const R deta2 = R(0.3);
+        const R bound1 = trp + deta2;
+        if (e < bound1) {
+          c = rh3 + (rh2 - rh3) * (e - trp) / deta2;
+        } else {
+          const R deta1 = R(0.09) + R(0.16) * (R(0.4) - trp) / R(0.3);
+          const R bound2 = R(1) - deta1;
+          if (e < bound2)
+            c = rh2;
+          else
+            c = rh1 + (rh2 - rh1) * R(std::sqrt((R(1) - e) / deta1));
+        }
+      }
+      crh2[size_t(k) * size_t(nw + 1) + j] = c;
+    }
+  }
+}
+
+template <class R>
+int launch_saturation(const cs2_dims* d, const cs2_params* P, const void* ap, const void* t, void* qsat, cudaStream_t st) {
+  if (d->ncol == 0) return CS2_OK;
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, 1.0);
+  dim3 grid((unsigned)((d->ncol + kPointBlock - 1) / kPointBlock), (unsigned)d->nlev);
+  saturation_kernel<R><<<grid, kPointBlock, 0, st>>>(p, P->LPHYLIN, static_cast<const R*>(ap), static_cast<const R*>(t),
+                                                    static_cast<R*>(qsat), d->ncol, d->ncol_stride);
+  return check_cuda(cudaGetLastError(), "saturation launch");
+}
+
+template <class R>
+int launch_state(const cs2_dims* d, double f, int mode, int ignore_supsat, const void* const* in,
+                 const void* const* in_i, void* const* out, cudaStream_t st) {
+  if (d->ncol == 0) return CS2_OK;
+  StatePtrs<R> ptrs;
+  for (int n = 0; n < CS2_NSTATE; ++n) {
+    ptrs.in[n] = static_cast<const R*>(in[n]);
+    ptrs.in_i[n] = in_i ? static_cast<const R*>(in_i[n]) : nullptr;
+    ptrs.out[n] = static_cast<R*>(out[n]);
+  }
+  dim3 grid((unsigned)((d->ncol + kPointBlock - 1) / kPointBlock), (unsigned)(d->nlev + 1));
+  if (mode == 0)
+    state_increment_kernel<R><<<grid, kPointBlock, 0, st>>>(ptrs, R(f), ignore_supsat, d->ncol, d->ncol_stride);
+  else
+    perturbed_state_kernel<R><<<grid, kPointBlock, 0, st>>>(ptrs, R(f), d->ncol, d->ncol_stride);
+  return check_cuda(cudaGetLastError(), mode == 0 ? "state_increment launch" : "perturbed_state launch");
+}
+
+template <class R>
+int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
+              bool ad_ref, int32_t* jsel_out, cudaStream_t st) {
+  if (d->ncol == 0) return CS2_OK;
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
+  const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  const bool tetens = P->LPHYLIN || P->LDRAIN1D;
+#define CS2_LAUNCH_NL(E, T)                                                                                  \
+  nl_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, d->ncol, d->ncol_stride, d->nlev, \
+                                                              ad_ref ? 1 : 0, jsel_out)
+  if (evap && tetens) CS2_LAUNCH_NL(true, true);
+  else if (evap) CS2_LAUNCH_NL(true, false);
+  else if (tetens) CS2_LAUNCH_NL(false, true);
+  else CS2_LAUNCH_NL(false, false);
+#undef CS2_LAUNCH_NL
+  return check_cuda(cudaGetLastError(), "cloudsc2_nl launch");
+}
+
+int check_tl_ad_flags(const cs2_params* P, const char* what) {
+  if (P->LEVAPLS2 || P->LDRAIN1D)
+    return fail(CS2_ERR_UNSUPPORTED,
+                std::string(what) + ": the precipitation-evaporation branch (LEVAPLS2 / LDRAIN1D) is not implemented "
+                                    "for TL/AD; the reference's own TL/AD of that branch are mutually inconsistent "
+                                    "(see DESIGN.md)");
+  return CS2_OK;
+}
+
+cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+namespace {
+template <class R>
+int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
+              const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, cudaStream_t st) {
+  int32_t* jsel = static_cast<int32_t*>(ws);
+  const bool ad_ref = !P->AD_TL_PREDICATES;
+  if (int rc = launch_nl<R>(d, P, dt, tables, traj, ad_ref, jsel, st)) return rc;
+  if (d->ncol == 0) return CS2_OK;
+  cs2::ADSeeds<R> s;
+  s.tnd_t = static_cast<R*>(seeds->in_tnd_t_i); s.tnd_q = static_cast<R*>(seeds->in_tnd_q_i);
+  s.tnd_ql = static_cast<R*>(seeds->in_tnd_ql_i); s.tnd_qi = static_cast<R*>(seeds->in_tnd_qi_i);
+  s.clc = static_cast<R*>(seeds->in_clc_i); s.covptot = static_cast<R*>(seeds->in_covptot_i);
+  s.fhpsl = static_cast<R*>(seeds->in_fhpsl_i); s.fhpsn = static_cast<R*>(seeds->in_fhpsn_i);
+  s.fplsl = static_cast<R*>(seeds->in_fplsl_i); s.fplsn = static_cast<R*>(seeds->in_fplsn_i);
+  cs2::ADOut<R> a;
+  a.aph = static_cast<R*>(adj->out_aph_i); a.ap = static_cast<R*>(adj->out_ap_i); a.q = static_cast<R*>(adj->out_q_i);
+  a.qsat = static_cast<R*>(adj->out_qsat_i); a.t = static_cast<R*>(adj->out_t_i); a.ql = static_cast<R*>(adj->out_ql_i);
+  a.qi = static_cast<R*>(adj->out_qi_i); a.lude = static_cast<R*>(adj->out_lude_i); a.lu = static_cast<R*>(adj->out_lu_i);
+  a.mfu = static_cast<R*>(adj->out_mfu_i); a.mfd = static_cast<R*>(adj->out_mfd_i);
+  a.supsat = static_cast<R*>(adj->out_supsat_i); a.tnd_t = static_cast<R*>(adj->out_tnd_cml_t_i);
+  a.tnd_q = static_cast<R*>(adj->out_tnd_cml_q_i); a.tnd_ql = static_cast<R*>(adj->out_tnd_cml_ql_i);
+  a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
+  const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
+  ad_bwd_kernel<R><<<grid, kColumnBlock, 0, st>>>(cs2::make_dev_params<R>(*P, dt), tables, cs2::make_nl_fields<R>(*traj),
+                                                 s, a, jsel, d->ncol, d->ncol_stride, d->nlev);
+  return check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch");
+}
+}  // namespace
+
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int cs2_abi_version(void) { return CS2_ABI_VERSION; }
+
+const char* cs2_last_error(void) { return g_last_error.c_str(); }
+
+int cs2_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDeviceCount");
+  return n;
+}
+
+size_t cs2_level_tables_bytes(int32_t nlev, int32_t dtype) {
+  if (nlev < 1) return 0;
+  const size_t es = dtype == CS2_F32 ? 4 : 8;
+  return 16 + cs2::tables_align16(size_t(nlev) * es) + cs2::tables_align16(size_t(nlev) * size_t(nlev) * es) +
+         cs2::tables_align16(size_t(nlev) * 4);
+}
+
+int cs2_level_tables_build(const cs2_params* params, int32_t nlev, int32_t dtype, const void* eta_host,
+                           void* tables_host, size_t tables_bytes) {
+  if (!params || !eta_host || !tables_host) return fail(CS2_ERR_NULL_POINTER, "level_tables_build: NULL argument");
+  if (nlev < 1 || nlev > 4096 || (dtype != CS2_F64 && dtype != CS2_F32))
+    return fail(CS2_ERR_BAD_DIMS, "level_tables_build: bad nlev or dtype");
+  if (tables_bytes < cs2_level_tables_bytes(nlev, dtype))
+    return fail(CS2_ERR_WORKSPACE, "level_tables_build: tables buffer too small");
+  std::memset(tables_host, 0, tables_bytes);
+  if (dtype == CS2_F64)
+    build_tables<double>(*params, nlev, static_cast<const double*>(eta_host), tables_host);
+  else
+    build_tables<float>(*params, nlev, static_cast<const float*>(eta_host), tables_host);
+  return CS2_OK;
+}
+
+int cs2_saturation(const cs2_dims* dims, const cs2_params* params, const void* in_ap, const void* in_t,
+                   void* out_qsat, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params) return fail(CS2_ERR_NULL_POINTER, "saturation: params is NULL");
+  const void* ptrs[3] = {in_ap, in_t, out_qsat};
+  if (int rc = check_ptrs(ptrs, 3, "saturation")) return rc;
+  return dims->dtype == CS2_F64 ? launch_saturation<double>(dims, params, in_ap, in_t, out_qsat, as_stream(stream))
+                                : launch_saturation<float>(dims, params, in_ap, in_t, out_qsat, as_stream(stream));
+}
+
+int cs2_state_increment(const cs2_dims* dims, double f, int32_t ignore_supsat, const void* const in[CS2_NSTATE],
+                        void* const out_i[CS2_NSTATE], void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!in || !out_i) return fail(CS2_ERR_NULL_POINTER, "state_increment: NULL field array");
+  if (int rc = check_ptrs(in, CS2_NSTATE, "state_increment in")) return rc;
+  if (int rc = check_ptrs(const_cast<const void* const*>(out_i), CS2_NSTATE, "state_increment out")) return rc;
+  return dims->dtype == CS2_F64 ? launch_state<double>(dims, f, 0, ignore_supsat, in, nullptr, out_i, as_stream(stream))
+                                : launch_state<float>(dims, f, 0, ignore_supsat, in, nullptr, out_i, as_stream(stream));
+}
+
+int cs2_perturbed_state(const cs2_dims* dims, double f, const void* const in[CS2_NSTATE],
+                        const void* const in_i[CS2_NSTATE], void* const out[CS2_NSTATE], void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!in || !in_i || !out) return fail(CS2_ERR_NULL_POINTER, "perturbed_state: NULL field array");
+  if (int rc = check_ptrs(in, CS2_NSTATE, "perturbed_state in")) return rc;
+  if (int rc = check_ptrs(in_i, CS2_NSTATE, "perturbed_state in_i")) return rc;
+  if (int rc = check_ptrs(const_cast<const void* const*>(out), CS2_NSTATE, "perturbed_state out")) return rc;
+  return dims->dtype == CS2_F64 ? launch_state<double>(dims, f, 1, 0, in, in_i, out, as_stream(stream))
+                                : launch_state<float>(dims, f, 1, 0, in, in_i, out, as_stream(stream));
+}
+
+int cs2_nl(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+           const cs2_nl_fields* f, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_nl: params or level tables NULL");
+  if (int rc = check_nl_fields(f, "cloudsc2_nl fields")) return rc;
+  return dims->dtype == CS2_F64
+             ? launch_nl<double>(dims, params, dt, level_tables_dev, f, false, nullptr, as_stream(stream))
+             : launch_nl<float>(dims, params, dt, level_tables_dev, f, false, nullptr, as_stream(stream));
+}
+
+int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+           const cs2_nl_fields* traj, const cs2_nl_fields* pert, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl: params or level tables NULL");
+  if (int rc = check_nl_fields(traj, "cloudsc2_tl trajectory fields")) return rc;
+  if (int rc = check_nl_fields(pert, "cloudsc2_tl perturbation fields")) return rc;
+  if (int rc = check_tl_ad_flags(params, "cloudsc2_tl")) return rc;
+  if (dims->ncol == 0) return CS2_OK;
+  const unsigned grid = (unsigned)((dims->ncol + kColumnBlock - 1) / kColumnBlock);
+  if (dims->dtype == CS2_F64) {
+    tl_kernel<double><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
+        cs2::make_dev_params<double>(*params, dt), level_tables_dev, cs2::make_nl_fields<double>(*traj),
+        cs2::make_nl_fields<double>(*pert), dims->ncol, dims->ncol_stride, dims->nlev);
+  } else {
+    tl_kernel<float><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
+        cs2::make_dev_params<float>(*params, dt), level_tables_dev, cs2::make_nl_fields<float>(*traj),
+        cs2::make_nl_fields<float>(*pert), dims->ncol, dims->ncol_stride, dims->nlev);
+  }
+  return check_cuda(cudaGetLastError(), "cloudsc2_tl launch");
+}
+
+size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
+  (void)params;
+  if (!dims || dims->ncol_stride <= 0) return 0;
+  size_t bytes = size_t(dims->ncol_stride) * sizeof(int32_t);  // tropopause candidate per column
+  (void)mode;
+  return (bytes + 255) & ~size_t(255);
+}
+
+int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+           const cs2_nl_fields* traj, const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* workspace_dev,
+           size_t workspace_bytes, int32_t mode, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_ad: params or level tables NULL");
+  if (int rc = check_nl_fields(traj, "cloudsc2_ad trajectory fields")) return rc;
+  if (!seeds || !adj) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_ad: seeds or adjoint outputs NULL");
+  static_assert(sizeof(cs2_ad_seeds) == 10 * sizeof(void*), "cs2_ad_seeds layout");
+  static_assert(sizeof(cs2_ad_outputs) == 16 * sizeof(void*), "cs2_ad_outputs layout");
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(seeds), 10, "cloudsc2_ad seeds")) return rc;
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(adj), 16, "cloudsc2_ad adjoint outputs")) return rc;
+  if (int rc = check_tl_ad_flags(params, "cloudsc2_ad")) return rc;
+  if (mode != CS2_AD_RECOMPUTE && mode != CS2_AD_CHECKPOINT) return fail(CS2_ERR_BAD_DIMS, "cloudsc2_ad: unknown mode");
+  if (mode == CS2_AD_CHECKPOINT)
+    return fail(CS2_ERR_UNSUPPORTED, "cloudsc2_ad: CS2_AD_CHECKPOINT is not implemented yet; use CS2_AD_RECOMPUTE");
+  if (!workspace_dev || workspace_bytes < cs2_ad_workspace_bytes(dims, params, mode))
+    return fail(CS2_ERR_WORKSPACE, "cloudsc2_ad: workspace missing or too small");
+  return dims->dtype == CS2_F64
+             ? launch_ad<double>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, as_stream(stream))
+             : launch_ad<float>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, as_stream(stream));
+}
+
+static int taylor_blocks(const cs2_dims* dims) {
+  const int64_t n = dims->ncol * int64_t(dims->nlev + 1);
+  int64_t nb = (n + 256 * 8 - 1) / (256 * 8);
+  if (nb < 1) nb = 1;
+  if (nb > 148 * 8) nb = 148 * 8;
+  return int(nb);
+}
+
+size_t cs2_taylor_scratch_bytes(const cs2_dims* dims, int32_t nfields) {
+  if (!dims || nfields < 1) return 0;
+  return size_t(taylor_blocks(dims)) * size_t(nfields) * sizeof(double2);
+}
+
+int cs2_taylor_sums(const cs2_dims* dims, int32_t nfields, const void* const* a_dev, const void* const* b_dev,
+                    const void* const* c_dev, double* sums_dev, void* scratch_dev, size_t scratch_bytes,
+                    void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (nfields < 1 || nfields > kMaxRedFields) return fail(CS2_ERR_BAD_DIMS, "taylor_sums: nfields outside [1, 16]");
+  if (!a_dev || !sums_dev || !scratch_dev) return fail(CS2_ERR_NULL_POINTER, "taylor_sums: NULL argument");
+  if (scratch_bytes < cs2_taylor_scratch_bytes(dims, nfields)) return fail(CS2_ERR_WORKSPACE, "taylor_sums: scratch too small");
+  RedPtrs f;
+  for (int n = 0; n < kMaxRedFields; ++n) {
+    f.a[n] = n < nfields ? a_dev[n] : nullptr;
+    f.b[n] = (n < nfields && b_dev) ? b_dev[n] : nullptr;
+    f.c[n] = (n < nfields && c_dev) ? c_dev[n] : nullptr;
+  }
+  const int nb = taylor_blocks(dims);
+  dim3 grid((unsigned)nb, (unsigned)nfields);
+  double2* partial = static_cast<double2*>(scratch_dev);
+  if (dims->dtype == CS2_F64)
+    taylor_partial_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(f, dims->ncol, dims->ncol_stride, dims->nlev + 1, partial);
+  else
+    taylor_partial_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(f, dims->ncol, dims->ncol_stride, dims->nlev + 1, partial);
+  if (int rc = check_cuda(cudaGetLastError(), "taylor partial launch")) return rc;
+  taylor_final_kernel<<<nfields, 32, 0, as_stream(stream)>>>(partial, nb, sums_dev);
+  return check_cuda(cudaGetLastError(), "taylor final launch");
+}
+
+int cs2_symmetry_norms(const cs2_dims* dims, int32_t nfields, const void* const* a_dev, const void* const* b_dev,
+                       double* norm_dev, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (nfields < 1 || nfields > kMaxRedFields) return fail(CS2_ERR_BAD_DIMS, "symmetry_norms: nfields outside [1, 16]");
+  if (!a_dev || !b_dev || !norm_dev) return fail(CS2_ERR_NULL_POINTER, "symmetry_norms: NULL argument");
+  if (int rc = check_ptrs(a_dev, nfields, "symmetry_norms a")) return rc;
+  if (int rc = check_ptrs(b_dev, nfields, "symmetry_norms b")) return rc;
+  if (dims->ncol == 0) return CS2_OK;
+  RedPtrs f;
+  for (int n = 0; n < kMaxRedFields; ++n) {
+    f.a[n] = n < nfields ? a_dev[n] : nullptr;
+    f.b[n] = n < nfields ? b_dev[n] : nullptr;
+    f.c[n] = nullptr;
+  }
+  const unsigned grid = (unsigned)((dims->ncol + kColumnBlock - 1) / kColumnBlock);
+  if (dims->dtype == CS2_F64)
+    symmetry_norm_kernel<double><<<grid, kColumnBlock, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
+  else
+    symmetry_norm_kernel<float><<<grid, kColumnBlock, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
+  return check_cuda(cudaGetLastError(), "symmetry norm launch");
+}
+
+}  // extern "C"
