@@ -1,0 +1,98 @@
+"""`SymmetryTest` (reference: physics/adjoint/validation.py:43-231).
+
+Same orchestration as the reference; the per-column inner products <TL x, TL x> and
+<x, AD TL x> are computed on the device in fp64 (`reductions.symmetry_norms`), only the scalar
+max_i norm3 is all-reduced (MAX) when the columns are sharded."""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from ... import distributed
+from ...reductions import symmetry_norms
+from ..common.increment import StateIncrement
+from ..common.saturation import Saturation
+from ..tangent_linear.microphysics import Cloudsc2TL
+from .microphysics import Cloudsc2AD
+
+TL_TENDS = ("f_t_i", "f_q_i", "f_ql_i", "f_qi_i")
+TL_DIAGS = ("f_clc_i", "f_fhpsl_i", "f_fhpsn_i", "f_fplsl_i", "f_fplsn_i", "f_covptot_i")
+AD_TENDS = ("f_cml_t_i", "f_cml_q_i", "f_cml_ql_i", "f_cml_qi_i")
+AD_DIAGS = ("f_ap_i", "f_aph_i", "f_t_i", "f_q_i", "f_qsat_i", "f_ql_i", "f_qi_i", "f_lu_i", "f_lude_i", "f_mfd_i",
+            "f_mfu_i", "f_supsat_i")
+
+
+class SymmetryTest:
+    def __init__(self, computational_grid, factor, kflag, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                 yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
+                 ad_predicates=None):
+        self.f = factor
+        kw = dict(enable_checks=enable_checks, gt4py_config=gt4py_config)
+        self.saturation = Saturation(computational_grid, kflag, lphylin, yoethf_params, yomcst_params, **kw)
+        self.cloudsc2_tl = Cloudsc2TL(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                      yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, **kw)
+        self.cloudsc2_ad = Cloudsc2AD(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                      yrecldp_params, yrephli_params, yrncl_params, yrphnc_params,
+                                      ad_predicates=ad_predicates, **kw)
+        self.state_increment = StateIncrement(computational_grid, factor, ignore_supsat=True, **kw)
+        self.diags_sat: Dict[str, Any] = {}
+        self.state_i: Dict[str, Any] = {}
+        self.tends_tl: Dict[str, Any] = {}
+        self.diags_tl: Dict[str, Any] = {}
+        self.tends_ad: Dict[str, Any] = {}
+        self.diags_ad: Dict[str, Any] = {}
+        self.norm3_max: Optional[float] = None
+        self.norm3: Optional[torch.Tensor] = None
+
+    def __call__(self, state, timestep, enable_validation: bool = True, verbose: bool = True) -> Optional[bool]:
+        self.diags_sat = self.saturation(state, out=self.diags_sat)
+        state.update(self.diags_sat)
+        self.state_i = self.state_increment(state, out=self.state_i)
+        state.update(self.state_i)
+        self.tends_tl, self.diags_tl = self.cloudsc2_tl(
+            state, timestep, out_tendencies=self.tends_tl, out_diagnostics=self.diags_tl
+        )
+        norm1 = self.get_norm1(self.tends_tl, self.diags_tl) if enable_validation else None
+
+        self.add_tendencies_to_state(state, self.tends_tl)
+        state.update(self.diags_tl)
+        self.tends_ad, self.diags_ad = self.cloudsc2_ad(
+            state, timestep, out_tendencies=self.tends_ad, out_diagnostics=self.diags_ad
+        )
+        if not enable_validation:
+            return None
+
+        norm2 = self.get_norm2(self.state_i, self.tends_ad, self.diags_ad)
+        eps = float(np.finfo(self.saturation.gt4py_config.dtypes.float).eps)
+        diff = (norm1 - norm2).abs()
+        self.norm3 = torch.where(norm2 == 0, diff / eps, diff / (eps * norm2))
+        nmax = self.norm3.max().reshape(1) if self.norm3.numel() else torch.zeros(1, dtype=torch.float64, device=diff.device)
+        distributed.allreduce_max_(nmax)
+        self.norm3_max = float(nmax.item())
+        passed = self.norm3_max < 1e4
+        if verbose:
+            print("The symmetry test passed. HOORAY!" if passed else "The symmetry test failed.")
+            print(f"The maximum error is {self.norm3_max:.10e} times the machine epsilon.")
+        return passed
+
+    @staticmethod
+    def get_norm1(tends_tl, diags_tl) -> torch.Tensor:
+        """<TL x, TL x> per column (:167-181)."""
+        flds = [tends_tl[n] for n in TL_TENDS] + [diags_tl[n] for n in TL_DIAGS]
+        return symmetry_norms(flds, flds)
+
+    @staticmethod
+    def get_norm2(state_i, tends_ad, diags_ad) -> torch.Tensor:
+        """<x, AD TL x> per column (:183-215)."""
+        a = [state_i["f_tnd_" + n[2:]] for n in AD_TENDS] + [state_i[n] for n in AD_DIAGS]
+        b = [tends_ad[n] for n in AD_TENDS] + [diags_ad[n] for n in AD_DIAGS]
+        return symmetry_norms(a, b)
+
+    @staticmethod
+    def add_tendencies_to_state(state, tends_tl) -> None:
+        """(:222-231)"""
+        for x in ("t", "q", "ql", "qi"):
+            state[f"f_tnd_{x}"] = tends_tl[f"f_{x}"]
+            state[f"f_tnd_{x}_i"] = tends_tl[f"f_{x}_i"]

@@ -1,0 +1,140 @@
+"""`TaylorTest` (reference: physics/tangent_linear/validation.py:44-261).
+
+Same orchestration, scoring and messages as the reference; what changes is where the norms are
+computed: the global sums over (column, level) run on the device (`reductions.TaylorSums`) and, when
+the columns are sharded over several GPUs, are all-reduced ONCE after the last perturbation
+(2 x 10 fields x 10 factors doubles) instead of per field."""
+from __future__ import annotations
+
+import sys
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ... import distributed
+from ...framework.timing import timing
+from ...reductions import TaylorSums
+from ..common.increment import PerturbedState, StateIncrement
+from ..common.saturation import Saturation
+from ..nonlinear.microphysics import Cloudsc2NL
+from .microphysics import Cloudsc2TL
+
+TEND_NAMES = ("f_t", "f_q", "f_ql", "f_qi")
+DIAG_NAMES = ("f_clc", "f_fhpsl", "f_fhpsn", "f_fplsl", "f_fplsn", "f_covptot")
+
+
+class TaylorTest:
+    def __init__(self, computational_grid, factor1, factor2s, kflag, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                 yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config):
+        self.f1 = factor1
+        self.f2s = tuple(factor2s)
+        yrncl_params.LREGCL = False  # no regularization in the Taylor test (:84-85)
+        kw = dict(enable_checks=enable_checks, gt4py_config=gt4py_config)
+        self.saturation = Saturation(computational_grid, kflag, lphylin, yoethf_params, yomcst_params, **kw)
+        self.cloudsc2_nl = Cloudsc2NL(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                      yrecldp_params, yrephli_params, yrphnc_params, **kw)
+        self.cloudsc2_tl = Cloudsc2TL(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                      yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, **kw)
+        self.state_increment = StateIncrement(computational_grid, factor1, **kw)
+        self.perturbed_states = [PerturbedState(computational_grid, f2, **kw) for f2 in self.f2s]
+        self.diags_nl: Dict[str, Any] = {}
+        self.diags_nl_p: Dict[str, Any] = {}
+        self.diags_sat: Dict[str, Any] = {}
+        self.diags_tl: Dict[str, Any] = {}
+        self.state_i: Dict[str, Any] = {}
+        self.state_p: Dict[str, Any] = {}
+        self.tends_nl: Dict[str, Any] = {}
+        self.tends_nl_p: Dict[str, Any] = {}
+        self.tends_tl: Dict[str, Any] = {}
+        self._sums_op = TaylorSums()
+        self._sums: Optional[torch.Tensor] = None  # [len(f2s)][10 fields][2] doubles on the device
+
+    def __call__(self, state, timestep) -> None:
+        self.validate(self.run(state, timestep))
+
+    def run(self, state, timestep) -> np.ndarray:
+        with timing("run"):
+            self.diags_sat = self.saturation(state, out=self.diags_sat)
+            state.update(self.diags_sat)
+            # the reference hands `tends_tl` to this NL call (:155-157), so its `tends_nl` aliases the
+            # TL trajectory tendencies; they are bit-identical here (NL and TL evaluate the same
+            # trajectory function), so NL gets its own dict
+            self.tends_nl, self.diags_nl = self.cloudsc2_nl(
+                state, timestep, out_tendencies=self.tends_nl, out_diagnostics=self.diags_nl
+            )
+            self.state_i = self.state_increment(state, out=self.state_i)
+            state.update(self.state_i)
+            self.tends_tl, self.diags_tl = self.cloudsc2_tl(
+                state, timestep, out_tendencies=self.tends_tl, out_diagnostics=self.diags_tl
+            )
+
+        dev = self.tends_tl["f_t"].buffer.device
+        nfields = len(TEND_NAMES) + len(DIAG_NAMES)
+        self._sums = torch.zeros((len(self.f2s), nfields, 2), dtype=torch.float64, device=dev)
+        for i, perturbed_state in enumerate(self.perturbed_states):
+            with timing("run"):
+                self.state_p = perturbed_state(state, out=self.state_p)
+                self.state_p["time"] = state["time"]
+                self.state_p["f_eta"] = state["f_eta"]
+                self.tends_nl_p, self.diags_nl_p = self.cloudsc2_nl(
+                    self.state_p, timestep, out_tendencies=self.tends_nl_p, out_diagnostics=self.diags_nl_p
+                )
+            with timing("norms"):
+                self.accumulate_sums(i)
+
+        with timing("norms"):
+            distributed.allreduce_sum_(self._sums)  # one collective for the whole test
+            sums = self._sums.cpu().numpy()
+        return np.array([self.get_norm(i, sums[i]) for i in range(len(self.f2s))])
+
+    def accumulate_sums(self, i: int) -> None:
+        """Device part of get_field_norm (:252-261): SUM(F_nl_p - F_nl) and SUM(F_tl_i) per field."""
+        a: List[Any] = [self.tends_nl_p[n] for n in TEND_NAMES] + [self.diags_nl_p[n] for n in DIAG_NAMES]
+        b: List[Any] = [self.tends_nl[n] for n in TEND_NAMES] + [self.diags_nl[n] for n in DIAG_NAMES]
+        c: List[Any] = [self.tends_tl[n + "_i"] for n in TEND_NAMES] + [self.diags_tl[n + "_i"] for n in DIAG_NAMES]
+        self._sums_op(a, b, c, self._sums[i].reshape(-1))
+
+    def get_norm(self, i: int, sums: np.ndarray) -> float:
+        """Host part of get_norm / get_field_norm (:219-261) from the reduced sums."""
+        total_count, total_norm = 0, 0.0
+        for fld in range(sums.shape[0]):
+            den = abs(self.f2s[i] * sums[fld, 1])
+            norm = abs(sums[fld, 0]) / den if den > sys.float_info.epsilon else 0
+            total_count += norm > 0
+            total_norm += norm
+        return total_norm / total_count if total_count > 0 else 0
+
+    def validate(self, norms: np.ndarray, verbose: bool = True):
+        """Scoring of the V-shape (:183-217).  Returns (passed, code)."""
+        norms = np.array(norms, dtype=np.float64)
+        lines = [">>> Taylor test: Start"]
+        start = -1
+        for i in range(norms.size):
+            lines.append(f"  factor1 = {self.f1:.3e}, factor2 = {self.f2s[i]:.3e}, norm = {norms[i]:.10f}")
+            norms[i] = np.abs(1 - norms[i])
+            if start == -1 and norms[i] < 0.5:
+                start = i
+        if start == -1 or start > 3:
+            passed, test = False, 13
+            log = "The test failed with error 13."
+        else:
+            test = -10
+            negat = 1
+            for i in range(start, norms.size - 1):
+                tmp_negat = int(norms[i + 1] < norms[i])
+                if negat > tmp_negat:
+                    test += 10
+                negat = tmp_negat
+            if test == -10:
+                test = 11
+            if np.min(norms[start:]) > 1e-5:
+                test += 7
+            if np.min(norms[start:]) > 1e-6:
+                test += 5
+            passed = test <= 5
+            log = f"The test passed with penalty {test}. HOORAY!" if passed else f"The test failed with error {test}."
+        lines += ["<<< Taylor test: End", log]
+        if verbose:
+            print("\n".join(lines))
+        return passed, test

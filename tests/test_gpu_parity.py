@@ -1,0 +1,196 @@
+"""GPU (-m gpu): the product path -- components -> ctypes -> C ABI -> sm_100a kernels -- against
+the NumPy oracle on the same seeded inputs, against the committed fixtures, and through
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): field-scaled max error 1e-12 in fp64, 1e-5 in fp32 (2e-5 for
+the fp32 TL/AD perturbation fields, whose fp32 oracle carries the same rounding noise)."""
+import os
+from datetime import timedelta
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gh():
+    import gpu_harness
+
+    return gpu_harness
+
+
+def test_cuda_library_is_the_one_running():
+    from cloudsc2_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.cs2_device_count() >= 1
+    assert os.path.basename(_lib.LIB_PATH) == "libcloudsc2_b200.so" and os.path.exists(_lib.LIB_PATH)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("block", ["base", "cold"])
+def test_nl_tl_ad_match_oracle(block, dtype):
+    out = gh().run_components(block=block, dtype=dtype, ncol=100, ad_predicates="tl")
+    P = H.externals(LREGCL=True)
+    st = H.make_state(block, dtype)
+    _, _, n3, ref = H.oracle_symmetry(st, P, predicates="tl")
+    tol = H.TOL[np.dtype(dtype)]
+    tol_i = tol * (2 if dtype == np.float32 else 1)
+    assert np.array_equal(out["eta"], ref["state"]["f_eta"])
+    assert H.field_err(out["qsat"], ref["state"]["f_qsat"]) <= tol
+    tn, dg = H.onp.cloudsc2_nl(ref["state"], H.DT, P)
+    H.assert_fields_close(out["tends_nl"], tn, tol, "NL tendencies: ")
+    H.assert_fields_close(out["diags_nl"], dg, tol, "NL diagnostics: ")
+    H.assert_fields_close(out["state_i"], {k: v for k, v in ref["state"].items() if k.endswith("_i") and k in out["state_i"]}, tol)
+    H.assert_fields_close(out["tends_tl"], ref["tends_tl"], tol_i, "TL tendencies: ")
+    H.assert_fields_close(out["diags_tl"], ref["diags_tl"], tol_i, "TL diagnostics: ")
+    H.assert_fields_close(out["tends_ad"], ref["tends_ad"], tol_i, "AD tendencies: ")
+    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], tol_i, "AD diagnostics: ")
+    for k, v in out["seeds_after"].items():
+        assert not v.any(), f"AD did not consume seed {k}"
+    if dtype == np.float64:
+        assert out["symmetry_norm3_max"] < 1e4
+        np.testing.assert_allclose(out["norm1"], H.onp.symmetry_norm1(ref["tends_tl"], ref["diags_tl"]), rtol=1e-11)
+
+
+def test_ad_reference_predicates_match_literal_oracle():
+    out = gh().run_components(block="base", dtype=np.float64, ncol=100, ad_predicates="reference")
+    _, _, _, ref = H.oracle_symmetry(H.make_state("base"), H.externals(LREGCL=True), predicates="reference")
+    H.assert_fields_close(out["tends_ad"], ref["tends_ad"], 1e-12, "AD(reference) tendencies: ")
+    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], 1e-12, "AD(reference) diagnostics: ")
+
+
+@pytest.mark.parametrize("flags", [dict(levapls2=True), dict(ldrain1d=True), dict(lphylin=False)])
+def test_nl_flag_paths(flags):
+    out = gh().run_components(block="base", dtype=np.float64, ncol=100, nl_only=True, **flags)
+    P = H.externals(LEVAPLS2=flags.get("levapls2", False), LDRAIN1D=flags.get("ldrain1d", False),
+                    LPHYLIN=flags.get("lphylin", True))
+    s = H.with_diagnostics(H.make_state("base"), P)
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    H.assert_fields_close(out["tends_nl"], tn, 1e-12, f"NL {flags}: ")
+    H.assert_fields_close(out["diags_nl"], dg, 1e-12, f"NL {flags}: ")
+    if flags.get("levapls2") or flags.get("ldrain1d"):
+        assert out["diags_nl"]["f_covptot"].any()
+
+
+def test_tl_ad_refuse_evaporation_flags_loudly():
+    from cloudsc2_b200._lib import CUDAExtensionError
+
+    with pytest.raises(CUDAExtensionError, match="evaporation"):
+        gh().run_components(block="base", dtype=np.float64, ncol=32, levapls2=True)
+
+
+@pytest.mark.parametrize("block", ["base", "cold"])
+@pytest.mark.parametrize("precision,dtype", [("double", np.float64), ("single", np.float32)])
+def test_against_committed_fixtures(block, precision, dtype):
+    """Committed oracle outputs (tests/golden/oracle_*.npz, first 16 columns of each block)."""
+    ref = np.load(os.path.join(GOLDEN, f"oracle_{block}_{precision}.npz"))
+    out = gh().run_components(block=block, dtype=dtype, ncol=16, ad_predicates="tl")
+    tol = H.TOL[np.dtype(dtype)]
+    tol_i = tol * (2 if dtype == np.float32 else 1)
+    H.assert_fields_close(out["tends_nl"], {k[5:]: ref[k] for k in ref.files if k.startswith("nl_t_")}, tol)
+    H.assert_fields_close(out["diags_nl"], {k[5:]: ref[k] for k in ref.files if k.startswith("nl_d_")}, tol)
+    H.assert_fields_close(out["tends_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_t_")}, tol_i)
+    H.assert_fields_close(out["diags_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_d_")}, tol_i)
+    H.assert_fields_close(out["tends_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_t_")}, tol_i)
+    H.assert_fields_close(out["diags_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_d_")}, tol_i)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_taylor_test_vshape(dtype):
+    """TL Taylor test with device-side sums: V-shape with slope 2 (reference scoring, penalty <= 5)."""
+    tt, norms = gh().run_taylor("base", dtype, ncol=1000)
+    passed, code = tt.validate(norms.copy(), verbose=False)
+    if dtype == np.float64:
+        assert passed and code <= 5, (norms, code)
+        err = np.abs(1 - norms)
+        assert 0.05 < err[4] / err[3] < 0.2 and 0.05 < err[5] / err[4] < 0.2, err
+        ref_norms, _ = H.oracle_taylor(H.make_state("base", ncol=1000), H.externals())
+        np.testing.assert_allclose(norms[:6], ref_norms[:6], rtol=1e-6)
+    else:
+        assert abs(1 - norms[1]) < 0.1 and abs(1 - norms[2]) < 0.05, norms  # fp32 bottoms out early
+
+
+@pytest.mark.parametrize("block", ["base", "cold"])
+def test_symmetry_test_at_roundoff(block):
+    st, passed = gh().run_symmetry(block, np.float64, ncol=1000)
+    assert passed and st.norm3_max < 1e4, st.norm3_max
+
+
+@pytest.mark.parametrize("ncol", [1, 31, 33, 257])
+def test_ragged_column_counts(ncol):
+    out = gh().run_components(block="base", dtype=np.float64, ncol=ncol)
+    P = H.externals(LREGCL=True)
+    _, _, _, ref = H.oracle_symmetry(H.make_state("base", ncol=ncol), P, predicates="tl")
+    tn, dg = H.onp.cloudsc2_nl(ref["state"], H.DT, P)
+    H.assert_fields_close(out["tends_nl"], tn, 1e-12)
+    H.assert_fields_close(out["diags_nl"], dg, 1e-12)
+    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], 1e-12)
+
+
+def test_full_size_tiling_property_65536():
+    """BASELINE config 2/3/4 size: every replicated 100-column block must be bit-identical, and the
+    first block must equal the oracle (size-independent property)."""
+    out = gh().run_components(block="base", dtype=np.float64, ncol=65536)
+    for group in ("tends_nl", "diags_nl", "tends_tl", "diags_tl", "tends_ad", "diags_ad"):
+        for k, v in out[group].items():
+            first = v[:, :100]
+            blocks = v[:, : 655 * 100].reshape(v.shape[0], 655, 100)
+            assert np.array_equal(blocks, np.broadcast_to(first[:, None, :], blocks.shape)), f"{group}.{k}"
+    P = H.externals(LREGCL=True)
+    _, _, _, ref = H.oracle_symmetry(H.make_state("base"), P, predicates="tl")
+    H.assert_fields_close({k: v[:, :100] for k, v in out["diags_ad"].items()}, ref["diags_ad"], 1e-12)
+    assert out["symmetry_norm3_max"] < 1e4
+
+
+def test_outputs_reused_and_padding_untouched():
+    """Second call into the same output dicts gives the same answer; the padding level of full-level
+    outputs and the padding columns beyond nx stay zero."""
+    g = gh()
+    from cloudsc2_b200 import iox
+    from cloudsc2_b200.physics.common.saturation import Saturation
+    from cloudsc2_b200.physics.nonlinear.microphysics import Cloudsc2NL
+
+    cfg, grid, state = g.make_grid_state("base", np.float64, 100)
+    p = iox.ifs_defaults()
+    state.update(Saturation(grid, 1, True, p["yoethf"], p["yomcst"], gt4py_config=cfg)(state))
+    nl = Cloudsc2NL(grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrphnc"], gt4py_config=cfg)
+    dt = timedelta(seconds=H.DT)
+    tn, dg = nl(state, dt)
+    first = {k: v.numpy() for k, v in {**tn, **dg}.items() if hasattr(v, "numpy")}
+    tn2, dg2 = nl(state, dt, out_tendencies=tn, out_diagnostics=dg)
+    assert tn2 is tn and dg2 is dg
+    for k, v in first.items():
+        now = {**tn, **dg}[k]
+        assert np.array_equal(now.numpy(), v), k
+        assert not now.buffer[:, 100:].any().item(), f"{k}: padding columns written"
+    for k in ("f_t", "f_q", "f_ql", "f_qi"):
+        assert not tn[k].buffer[137].any().item(), f"{k}: padding level written"
+    assert not dg["f_clc"].buffer[137].any().item()
+
+
+def test_reductions_match_numpy():
+    from cloudsc2_b200.framework.config import GridConfig
+    from cloudsc2_b200.framework.grid import ComputationalGrid, I, J, K
+    from cloudsc2_b200.framework.storage import zeros
+    from cloudsc2_b200.reductions import TaylorSums, symmetry_norms
+
+    g = gh()
+    rng = np.random.default_rng(3)
+    for dtype in (np.float64, np.float32):
+        cfg = g.config_for(dtype)
+        grid = ComputationalGrid(GridConfig(nx=777, ny=1, nz=137))
+        arrs = [rng.normal(size=(138, 777)).astype(dtype) for _ in range(6)]
+        flds = [zeros(grid, (I, J, K - 1 / 2), gt4py_config=cfg).assign(a) for a in arrs]
+        sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+        TaylorSums()([flds[0], flds[1]], [flds[2], flds[3]], [flds[4], flds[5]], sums)
+        ref = [np.sum(arrs[0].astype(np.float64) - arrs[2]), np.sum(arrs[4], dtype=np.float64),
+               np.sum(arrs[1].astype(np.float64) - arrs[3]), np.sum(arrs[5], dtype=np.float64)]
+        np.testing.assert_allclose(sums.cpu().numpy(), ref, rtol=1e-9, atol=1e-9)
+        n = symmetry_norms(flds[:3], flds[3:]).cpu().numpy()
+        refn = sum(np.sum(arrs[i].astype(np.float64) * arrs[i + 3], axis=0) for i in range(3))
+        np.testing.assert_allclose(n, refn, rtol=1e-9, atol=1e-9)

@@ -1,0 +1,102 @@
+"""CPU: the product's column code (csrc/cs2_columns.cuh, compiled for the host by oracle/Makefile)
+against the independent NumPy oracle.  This checks the kernel MATH without a GPU; the `-m gpu`
+tests check the same thing through the CUDA kernels."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+DTYPES = [np.float64, np.float32]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("block", ["base", "cold"])
+def test_twin_saturation_and_nl(block, dtype):
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state(block, dtype), P)
+    tol = H.TOL[np.dtype(dtype)]
+    assert H.field_err(H.twin_saturation(s["f_ap"], s["f_t"], P), s["f_qsat"]) <= tol
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P)
+    H.assert_fields_close(ttn, tn, tol, "NL tendencies: ")
+    H.assert_fields_close(tdg, dg, tol, "NL diagnostics: ")
+
+
+@pytest.mark.parametrize("flags", [dict(LEVAPLS2=True), dict(LDRAIN1D=True), dict(LPHYLIN=False),
+                                    dict(LPHYLIN=False, LEVAPLS2=True)])
+def test_twin_nl_flag_paths(flags):
+    """Evaporation branch and the non-LPHYLIN thermodynamics (NL only)."""
+    P = H.externals(**flags)
+    s = H.with_diagnostics(H.make_state("base"), P)
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P)
+    H.assert_fields_close(ttn, tn, 1e-12, f"NL {flags}: ")
+    H.assert_fields_close(tdg, dg, 1e-12, f"NL {flags}: ")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("block", ["base", "cold"])
+@pytest.mark.parametrize("lregcl", [True, False])
+def test_twin_tl(block, dtype, lregcl):
+    P = H.externals(LREGCL=lregcl)
+    s = H.with_diagnostics(H.make_state(block, dtype), P)
+    s.update(H.onp.state_increment(s, 0.01))
+    rt, rd = H.onp.cloudsc2_tl(s, H.DT, P)
+    tt, td = H.twin_tl(s, H.DT, P)
+    tol = H.TOL[np.dtype(dtype)] * (2 if dtype == np.float32 else 1)
+    H.assert_fields_close(tt, rt, tol, "TL tendencies: ")
+    H.assert_fields_close(td, rd, tol, "TL diagnostics: ")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("block,predicates", [("base", "tl"), ("base", "reference"), ("cold", "tl")])
+def test_twin_ad(block, predicates, dtype):
+    P = H.externals(LREGCL=True)
+    _, _, _, o = H.oracle_symmetry(H.make_state(block, dtype), P, predicates=predicates)
+    ad_in = dict(o["state"])
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = o["tends_tl"][f"f_{x}_i"].copy()
+    for k, v in o["diags_tl"].items():
+        ad_in[k] = v.copy()
+    tad, dad, consumed = H.twin_ad(ad_in, H.DT, P, predicates=predicates)
+    tol = H.TOL[np.dtype(dtype)] * (2 if dtype == np.float32 else 1)
+    H.assert_fields_close(tad, o["tends_ad"], tol, "AD tendencies: ")
+    H.assert_fields_close(dad, o["diags_ad"], tol, "AD diagnostics: ")
+    for k, v in consumed.items():
+        assert not v.any(), f"seed {k} not zeroed"
+
+
+def test_twin_symmetry_at_roundoff():
+    """<TL x, TL x> = <x, AD TL x> per column, with the product's own TL and AD."""
+    P = H.externals(LREGCL=True)
+    s = H.with_diagnostics(H.make_state("base"), P)
+    si = H.onp.state_increment(s, 0.01, ignore_supsat=True)
+    s.update(si)
+    tt, td = H.twin_tl(s, H.DT, P)
+    n1 = H.onp.symmetry_norm1(tt, td)
+    ad_in = dict(s)
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = tt[f"f_{x}_i"].copy()
+    ad_in.update({k: v.copy() for k, v in td.items()})
+    tad, dad, _ = H.twin_ad(ad_in, H.DT, P, predicates="tl")
+    n3 = H.onp.symmetry_norm3(n1, H.onp.symmetry_norm2(si, tad, dad), np.float64)
+    assert n3.max() < 1e4, n3.max()
+
+
+def test_twin_tiled_blocks_are_bit_identical():
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state("base", ncol=300), P)
+    tn, dg = H.twin_nl(s, H.DT, P)
+    for d in (tn, dg):
+        for k, v in d.items():
+            assert np.array_equal(v[:, :100], v[:, 100:200]) and np.array_equal(v[:, :100], v[:, 200:300]), k
+
+
+@pytest.mark.parametrize("ncol", [1, 31, 33])
+def test_twin_ragged_column_counts(ncol):
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state("base", ncol=ncol), P)
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P)
+    H.assert_fields_close(ttn, tn, 1e-12)
+    H.assert_fields_close(tdg, dg, 1e-12)
