@@ -76,7 +76,7 @@ class ClockSampler:
             os.close(fd)
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -253,12 +253,19 @@ def run_gpu_arm(args):
         sat(state, out=diags)
         nl(state, dt, out_tendencies=tends, out_diagnostics=diags_nl)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(torch.cuda.current_device()) as clocks:
+        # the sampler (20 ms period) spans warm-up + timed region: the timed region alone lasts only
+        # steps x ~0.5 ms, so the warm-up is repeated until >= 0.25 s of load precede it
+        t_load = time.perf_counter()
+        nwarm = 0
+        while nwarm < args.warmup or time.perf_counter() - t_load < 0.25:
+            step()
+            nwarm += 1
+            if nwarm % 16 == 0:
+                torch.cuda.synchronize()
+        barrier()
         t_start.record()
         for a, b in ev:
             sat(state, out=diags)
@@ -390,7 +397,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--columns", type=int, default=65536, help="columns per GPU")
     ap.add_argument("--precision", choices=("double", "single"), default="double")

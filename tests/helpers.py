@@ -55,9 +55,29 @@ def field_err(a: np.ndarray, b: np.ndarray) -> float:
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) / scale
 
 
-def assert_fields_close(got: Dict[str, np.ndarray], ref: Dict[str, np.ndarray], tol: float, what: str = "") -> None:
+def fp32_field_tolerances(ref32: Dict[str, np.ndarray], ref64: Dict[str, np.ndarray], base: float = 1e-5,
+                          factor: float = 4.0) -> Dict[str, float]:
+    """Per-field tolerance for fp32 runs: BASELINE's 1e-5, widened -- only where needed -- to `factor` x the
+    error the reference's OWN fp32 execution (the fp32 oracle) has against the fp64 oracle on the same
+    inputs.  The TL/AD perturbation fields are differences of nearly equal quantities; there the fp32 oracle
+    itself is only accurate to ~1e-5 of the field maximum, so two correct fp32 implementations (different
+    libm, different but equivalent operation order) differ from each other by a small multiple of that.
+    The NL outputs are always held to the plain 1e-5."""
+    tol = {}
+    for name, r32 in ref32.items():
+        r64 = ref64.get(name)
+        own = field_err(r32, r64) if r64 is not None and np.max(np.abs(r64)) > 0 else 0.0
+        tol[name] = max(base, factor * own)
+    return tol
+
+
+def assert_fields_close(got: Dict[str, np.ndarray], ref: Dict[str, np.ndarray], tol, what: str = "") -> None:
+    """`tol`: one number, or a dict of per-field tolerances (see fp32_field_tolerances)."""
     bad = []
+    tols = tol if isinstance(tol, dict) else None
     for name, r in ref.items():
+        if tols is not None:
+            tol = tols[name]
         g = got[name]
         assert g.shape == r.shape, f"{what}{name}: shape {g.shape} != {r.shape}"
         if not np.all(np.isfinite(g)):

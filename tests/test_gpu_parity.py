@@ -2,8 +2,9 @@
 the NumPy oracle on the same seeded inputs, against the committed fixtures, and through
 size-independent properties at BASELINE.json's full sizes.
 
-Tolerances (BASELINE.json north_star): field-scaled max error 1e-12 in fp64, 1e-5 in fp32 (2e-5 for
-the fp32 TL/AD perturbation fields, whose fp32 oracle carries the same rounding noise)."""
+Tolerances (BASELINE.json north_star): field-scaled max error 1e-12 in fp64; 1e-5 in fp32, widened per
+field only where the fp32 oracle itself is further than that from the fp64 oracle
+(helpers.fp32_field_tolerances: max(1e-5, 4 x the fp32 oracle's own error); NL always 1e-5)."""
 import os
 from datetime import timedelta
 
@@ -39,17 +40,21 @@ def test_nl_tl_ad_match_oracle(block, dtype):
     st = H.make_state(block, dtype)
     _, _, n3, ref = H.oracle_symmetry(st, P, predicates="tl")
     tol = H.TOL[np.dtype(dtype)]
-    tol_i = tol * (2 if dtype == np.float32 else 1)
+    tol_i = {g: tol for g in ("tends_tl", "diags_tl", "tends_ad", "diags_ad")}
+    if dtype == np.float32:  # per-field fp32 tolerances from the fp64 oracle on the same (fp32-rounded) inputs
+        st64 = {k: v.astype(np.float64) for k, v in st.items()}
+        _, _, _, ref64 = H.oracle_symmetry(st64, P, predicates="tl")
+        tol_i = {g: H.fp32_field_tolerances(ref[g], ref64[g]) for g in tol_i}
     assert np.array_equal(out["eta"], ref["state"]["f_eta"])
     assert H.field_err(out["qsat"], ref["state"]["f_qsat"]) <= tol
     tn, dg = H.onp.cloudsc2_nl(ref["state"], H.DT, P)
     H.assert_fields_close(out["tends_nl"], tn, tol, "NL tendencies: ")
     H.assert_fields_close(out["diags_nl"], dg, tol, "NL diagnostics: ")
     H.assert_fields_close(out["state_i"], {k: v for k, v in ref["state"].items() if k.endswith("_i") and k in out["state_i"]}, tol)
-    H.assert_fields_close(out["tends_tl"], ref["tends_tl"], tol_i, "TL tendencies: ")
-    H.assert_fields_close(out["diags_tl"], ref["diags_tl"], tol_i, "TL diagnostics: ")
-    H.assert_fields_close(out["tends_ad"], ref["tends_ad"], tol_i, "AD tendencies: ")
-    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], tol_i, "AD diagnostics: ")
+    H.assert_fields_close(out["tends_tl"], ref["tends_tl"], tol_i["tends_tl"], "TL tendencies: ")
+    H.assert_fields_close(out["diags_tl"], ref["diags_tl"], tol_i["diags_tl"], "TL diagnostics: ")
+    H.assert_fields_close(out["tends_ad"], ref["tends_ad"], tol_i["tends_ad"], "AD tendencies: ")
+    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], tol_i["diags_ad"], "AD diagnostics: ")
     for k, v in out["seeds_after"].items():
         assert not v.any(), f"AD did not consume seed {k}"
     if dtype == np.float64:
@@ -91,13 +96,20 @@ def test_against_committed_fixtures(block, precision, dtype):
     ref = np.load(os.path.join(GOLDEN, f"oracle_{block}_{precision}.npz"))
     out = gh().run_components(block=block, dtype=dtype, ncol=16, ad_predicates="tl")
     tol = H.TOL[np.dtype(dtype)]
-    tol_i = tol * (2 if dtype == np.float32 else 1)
+    ref64 = np.load(os.path.join(GOLDEN, f"oracle_{block}_double.npz"))
+
+    def tol_for(prefix):
+        r = {k[len(prefix):]: ref[k] for k in ref.files if k.startswith(prefix)}
+        if dtype == np.float64:
+            return {k: tol for k in r}
+        return H.fp32_field_tolerances(r, {k[len(prefix):]: ref64[k] for k in ref64.files if k.startswith(prefix)})
+
     H.assert_fields_close(out["tends_nl"], {k[5:]: ref[k] for k in ref.files if k.startswith("nl_t_")}, tol)
     H.assert_fields_close(out["diags_nl"], {k[5:]: ref[k] for k in ref.files if k.startswith("nl_d_")}, tol)
-    H.assert_fields_close(out["tends_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_t_")}, tol_i)
-    H.assert_fields_close(out["diags_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_d_")}, tol_i)
-    H.assert_fields_close(out["tends_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_t_")}, tol_i)
-    H.assert_fields_close(out["diags_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_d_")}, tol_i)
+    H.assert_fields_close(out["tends_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_t_")}, tol_for("tl_t_"))
+    H.assert_fields_close(out["diags_tl"], {k[5:]: ref[k] for k in ref.files if k.startswith("tl_d_")}, tol_for("tl_d_"))
+    H.assert_fields_close(out["tends_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_t_")}, tol_for("ad_tl_t_"))
+    H.assert_fields_close(out["diags_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_d_")}, tol_for("ad_tl_d_"))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
