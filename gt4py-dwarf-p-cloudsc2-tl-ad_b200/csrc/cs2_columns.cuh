@@ -66,11 +66,13 @@ CS2_HD int tropopause_candidate(const DevParams<R>& p, const LevelTables<R>& tab
 
 template <class R>
 CS2_HD void load_level(const NLFields<R>& f, int64_t S, int64_t i, int k, R aph0, LevelIn<R>& in) {
-  const int64_t o = int64_t(k) * S + i;
+  // 32-bit element offsets ((nlev+1) * ncol_stride < 2^32 is checked by the launcher): one IMAD.WIDE per address
+  const uint32_t o = uint32_t(k) * uint32_t(S) + uint32_t(i);
+  const uint32_t S32 = uint32_t(S);
   in.ap = f.ap[o];
   in.aph0 = aph0;
-  in.aph1 = f.aph[o + S];
-  in.lu1 = f.lu[o + S];
+  in.aph1 = f.aph[o + S32];
+  in.lu1 = f.lu[o + S32];
   in.lude = f.lude[o];
   in.mfd = f.mfd[o];
   in.mfu = f.mfu[o];
@@ -99,16 +101,21 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
   Carry<R> c{R(0), R(0), R(0)};
   const R aph_s = f.aph[int64_t(nlev) * S + i];
   R aph0 = f.aph[i];
-  // half level 0: enthalpy fluxes are zero (:391-394); NL leaves fplsl/fplsn[0] untouched
+  // half level 0: enthalpy fluxes are zero (:391-394); NL leaves fplsl/fplsn[0] untouched,
+  // the AD stencil (jsel_out != nullptr) writes them too (AD :466-470)
   f.fhpsl[i] = R(0);
   f.fhpsn[i] = R(0);
+  if (jsel_out) {
+    f.fplsl[i] = R(0);
+    f.fplsn[i] = R(0);
+  }
   for (int k = 0; k < nlev; ++k) {
     LevelIn<R> in;
     load_level(f, S, i, k, aph0, in);
     LevelOut<R> o;
     Traj<R> tr;
     level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
-    const int64_t off = int64_t(k) * S + i;
+    const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     f.clc[off] = o.clc;
     f.covptot[off] = o.covptot;
     f.o_tnd_q[off] = o.tnd_q;
@@ -116,10 +123,11 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     f.o_tnd_ql[off] = o.tnd_ql;
     f.o_tnd_t[off] = o.tnd_t;
     // fluxes shifted one half level down (:395-399)
-    f.fplsl[off + S] = c.rfl;
-    f.fplsn[off + S] = c.sfl;
-    f.fhpsl[off + S] = -c.rfl * p.RLVTT;
-    f.fhpsn[off + S] = -c.sfl * p.RLSTT;
+    const uint32_t offn = off + uint32_t(S);
+    f.fplsl[offn] = c.rfl;
+    f.fplsn[offn] = c.sfl;
+    f.fhpsl[offn] = -c.rfl * p.RLVTT;
+    f.fhpsn[offn] = -c.sfl * p.RLSTT;
     aph0 = in.aph1;
   }
 }
@@ -148,17 +156,18 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     Traj<R> tr;
     level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr);
     level_tl<R>(p, in, d, tr, ci, oi);
-    const int64_t off = int64_t(k) * S + i;
+    const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
+    const uint32_t offn = off + uint32_t(S);
     f.clc[off] = o.clc;          g.clc[off] = oi.clc;
     f.covptot[off] = o.covptot;  g.covptot[off] = oi.covptot;
     f.o_tnd_q[off] = o.tnd_q;    g.o_tnd_q[off] = oi.tnd_q;
     f.o_tnd_qi[off] = o.tnd_qi;  g.o_tnd_qi[off] = oi.tnd_qi;
     f.o_tnd_ql[off] = o.tnd_ql;  g.o_tnd_ql[off] = oi.tnd_ql;
     f.o_tnd_t[off] = o.tnd_t;    g.o_tnd_t[off] = oi.tnd_t;
-    f.fplsl[off + S] = c.rfl;            g.fplsl[off + S] = ci.rfl;
-    f.fplsn[off + S] = c.sfl;            g.fplsn[off + S] = ci.sfl;
-    f.fhpsl[off + S] = -c.rfl * p.RLVTT; g.fhpsl[off + S] = -ci.rfl * p.RLVTT;
-    f.fhpsn[off + S] = -c.sfl * p.RLSTT; g.fhpsn[off + S] = -ci.sfl * p.RLSTT;
+    f.fplsl[offn] = c.rfl;            g.fplsl[offn] = ci.rfl;
+    f.fplsn[offn] = c.sfl;            g.fplsn[offn] = ci.sfl;
+    f.fhpsl[offn] = -c.rfl * p.RLVTT; g.fhpsl[offn] = -ci.rfl * p.RLVTT;
+    f.fhpsn[offn] = -c.sfl * p.RLSTT; g.fhpsn[offn] = -ci.sfl * p.RLSTT;
     aph0 = in.aph1;
     aph0_i = d.aph1;
   }
@@ -183,7 +192,8 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
   R a_dp_below = R(0);            // a_dp of level k+1 (0 below the surface: tmp_aph_s_i = 0)
   R aph1 = aph_s;
   for (int k = nlev - 1; k >= 0; --k) {
-    const int64_t off = int64_t(k) * S + i;
+    const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
+    const uint32_t offn = off + uint32_t(S);
     LevelIn<R> in;
     const R aph0 = f.aph[off];
     load_level(f, S, i, k, aph0, in);
@@ -205,10 +215,10 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     so.tnd_qi = s.tnd_qi[off]; s.tnd_qi[off] = R(0);
     so.clc = s.clc[off];       s.clc[off] = R(0);
     so.covptot = R(0);         s.covptot[off] = R(0);
-    R a_rfln = a_rfl + (s.fplsl[off + S] - s.fhpsl[off + S] * p.RLVTT);
-    R a_sfln = a_sfl + (s.fplsn[off + S] - s.fhpsn[off + S] * p.RLSTT);
-    s.fplsl[off + S] = R(0); s.fhpsl[off + S] = R(0);
-    s.fplsn[off + S] = R(0); s.fhpsn[off + S] = R(0);
+    R a_rfln = a_rfl + (s.fplsl[offn] - s.fhpsl[offn] * p.RLVTT);
+    R a_sfln = a_sfl + (s.fplsn[offn] - s.fhpsn[offn] * p.RLSTT);
+    s.fplsl[offn] = R(0); s.fhpsl[offn] = R(0);
+    s.fplsn[offn] = R(0); s.fhpsn[offn] = R(0);
 
     LevelIn<R> ad;
     level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
@@ -223,8 +233,8 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     a.ap[off] = ad.ap;         a.lude[off] = ad.lude;
     a.mfu[off] = ad.mfu;       a.mfd[off] = ad.mfd;
     // staggered fields (AD :969-986): aph_i[k+1] = a_dp(k) - a_dp(k+1); lu_i[k+1] = adjoint of lu[k+1]
-    a.aph[off + S] = ad.aph1 - a_dp_below;
-    a.lu[off + S] = ad.lu1;
+    a.aph[offn] = ad.aph1 - a_dp_below;
+    a.lu[offn] = ad.lu1;
     a_dp_below = ad.aph1;
     aph1 = aph0;
   }

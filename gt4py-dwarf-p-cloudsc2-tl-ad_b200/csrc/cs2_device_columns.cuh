@@ -1,0 +1,278 @@
+// Device-only column sweeps with a two-stage cp.async prefetch ring.
+//
+// Same level physics as cs2_columns.cuh (level_fwd / level_tl / level_ad); what differs is the
+// data movement.  A thread owns a column and, while it computes level k (several thousand cycles of
+// dependent FP64 work), the 16 / 32 / 27 inputs of the next level are already in flight: they are
+// copied global -> shared with cp.async (LDGSTS) into a slot private to the thread
+// (`stage[s][field][tid]`, conflict-free, no __syncthreads needed: a thread only ever reads what it
+// copied itself, after cp.async.wait_group 0).  This hides the HBM latency without spending a
+// single register on the prefetch, which matters because the register budget decides whether all
+// 65 536 columns of the headline case are resident in one wave.
+#pragma once
+
+#include "cs2_columns.cuh"
+
+namespace cs2 {
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// N input streams, all indexed with the same element offset `k * S + i` (fields that are read at
+// level k+1 are passed with their base pointer advanced by S on the host side).
+template <class R, int N>
+struct Streams {
+  const R* p[N];
+};
+
+template <class R, int N, int BLOCK>
+struct Ring {
+  R v[2][N][BLOCK];
+};
+
+template <class R, int N, int BLOCK>
+__device__ __forceinline__ void ring_issue(Ring<R, N, BLOCK>& ring, const Streams<R, N>& in, int stage, uint32_t off) {
+#pragma unroll
+  for (int f = 0; f < N; ++f) cp_async<sizeof(R)>(&ring.v[stage][f][threadIdx.x], in.p[f] + off);
+  cp_async_commit();
+}
+
+// order of the NL input streams
+enum { I_AP, I_APH1, I_LU1, I_LUDE, I_MFD, I_MFU, I_Q, I_QI, I_QL, I_QSAT, I_SUPSAT, I_T, I_TQ, I_TQI, I_TQL, I_TT, I_NL };
+
+template <class R>
+inline Streams<R, I_NL> nl_streams(const NLFields<R>& f, int64_t S) {
+  Streams<R, I_NL> s;
+  s.p[I_AP] = f.ap; s.p[I_APH1] = f.aph + S; s.p[I_LU1] = f.lu + S; s.p[I_LUDE] = f.lude; s.p[I_MFD] = f.mfd;
+  s.p[I_MFU] = f.mfu; s.p[I_Q] = f.q; s.p[I_QI] = f.qi; s.p[I_QL] = f.ql; s.p[I_QSAT] = f.qsat;
+  s.p[I_SUPSAT] = f.supsat; s.p[I_T] = f.t; s.p[I_TQ] = f.tnd_q; s.p[I_TQI] = f.tnd_qi; s.p[I_TQL] = f.tnd_ql;
+  s.p[I_TT] = f.tnd_t;
+  return s;
+}
+
+template <class R, int N, int BLOCK>
+__device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, int stage, int base, R aph0, LevelIn<R>& in) {
+  const int t = threadIdx.x;
+  in.ap = ring.v[stage][base + I_AP][t];
+  in.aph0 = aph0;
+  in.aph1 = ring.v[stage][base + I_APH1][t];
+  in.lu1 = ring.v[stage][base + I_LU1][t];
+  in.lude = ring.v[stage][base + I_LUDE][t];
+  in.mfd = ring.v[stage][base + I_MFD][t];
+  in.mfu = ring.v[stage][base + I_MFU][t];
+  in.q = ring.v[stage][base + I_Q][t];
+  in.qi = ring.v[stage][base + I_QI][t];
+  in.ql = ring.v[stage][base + I_QL][t];
+  in.qsat = ring.v[stage][base + I_QSAT][t];
+  in.supsat = ring.v[stage][base + I_SUPSAT][t];
+  in.t = ring.v[stage][base + I_T][t];
+  in.tnd_q = ring.v[stage][base + I_TQ][t];
+  in.tnd_qi = ring.v[stage][base + I_TQI][t];
+  in.tnd_ql = ring.v[stage][base + I_TQL][t];
+  in.tnd_t = ring.v[stage][base + I_TT][t];
+}
+
+// ---------------------------------------------------------------------------------------
+// NL (and AD forward when jsel_out != nullptr)
+// ---------------------------------------------------------------------------------------
+template <class R, class C, int BLOCK>
+__device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                              const Streams<R, I_NL>& in_s, Ring<R, I_NL, BLOCK>& ring, uint32_t S,
+                                              int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out) {
+  ring_issue(ring, in_s, 0, i);  // level 0 is in flight while the tropopause scan runs
+  const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
+  if (jsel_out && valid) jsel_out[i] = jsel;
+  const int ncand = tab.nw + 1;
+
+  Carry<R> c{R(0), R(0), R(0)};
+  const R aph_s = f.aph[uint32_t(nlev) * S + i];
+  R aph0 = f.aph[i];
+  if (valid) {
+    f.fhpsl[i] = R(0);
+    f.fhpsn[i] = R(0);
+    if (jsel_out) {  // the AD stencil also writes the level-0 precipitation fluxes (AD :466-470)
+      f.fplsl[i] = R(0);
+      f.fplsn[i] = R(0);
+    }
+  }
+  for (int k = 0; k < nlev; ++k) {
+    const uint32_t off = uint32_t(k) * S + i;
+    cp_async_wait_all();
+    LevelIn<R> in;
+    ring_read_level(ring, k & 1, 0, aph0, in);
+    if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
+    LevelOut<R> o;
+    Traj<R> tr;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    if (valid) {
+      f.clc[off] = o.clc;
+      f.covptot[off] = o.covptot;
+      f.o_tnd_q[off] = o.tnd_q;
+      f.o_tnd_qi[off] = o.tnd_qi;
+      f.o_tnd_ql[off] = o.tnd_ql;
+      f.o_tnd_t[off] = o.tnd_t;
+      const uint32_t offn = off + S;
+      f.fplsl[offn] = c.rfl;
+      f.fplsn[offn] = c.sfl;
+      f.fhpsl[offn] = -c.rfl * p.RLVTT;
+      f.fhpsn[offn] = -c.sfl * p.RLSTT;
+    }
+    aph0 = in.aph1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// TL: streams [0, 16) = trajectory inputs, [16, 32) = perturbation inputs
+// ---------------------------------------------------------------------------------------
+template <class R>
+inline Streams<R, 2 * I_NL> tl_streams(const NLFields<R>& f, const NLFields<R>& g, int64_t S) {
+  Streams<R, 2 * I_NL> s;
+  const Streams<R, I_NL> a = nl_streams(f, S), b = nl_streams(g, S);
+  for (int n = 0; n < I_NL; ++n) {
+    s.p[n] = a.p[n];
+    s.p[I_NL + n] = b.p[n];
+  }
+  return s;
+}
+
+template <class R, int BLOCK>
+__device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                              const NLFields<R>& g, const Streams<R, 2 * I_NL>& in_s,
+                                              Ring<R, 2 * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
+                                              bool valid) {
+  using C = Cfg<false, true>;
+  ring_issue(ring, in_s, 0, i);
+  const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
+  const int ncand = tab.nw + 1;
+
+  Carry<R> c{R(0), R(0), R(0)}, ci{R(0), R(0), R(0)};
+  const R aph_s = f.aph[uint32_t(nlev) * S + i];
+  R aph0 = f.aph[i], aph0_i = g.aph[i];
+  if (valid) {  // half level 0 (TL :757-765)
+    f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
+    g.fplsl[i] = R(0); g.fplsn[i] = R(0); g.fhpsl[i] = R(0); g.fhpsn[i] = R(0);
+  }
+  for (int k = 0; k < nlev; ++k) {
+    const uint32_t off = uint32_t(k) * S + i;
+    cp_async_wait_all();
+    LevelIn<R> in, d;
+    ring_read_level(ring, k & 1, 0, aph0, in);
+    ring_read_level(ring, k & 1, I_NL, aph0_i, d);
+    if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
+    LevelOut<R> o, oi;
+    Traj<R> tr;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr);
+    level_tl<R>(p, in, d, tr, ci, oi);
+    if (valid) {
+      const uint32_t offn = off + S;
+      f.clc[off] = o.clc;          g.clc[off] = oi.clc;
+      f.covptot[off] = o.covptot;  g.covptot[off] = oi.covptot;
+      f.o_tnd_q[off] = o.tnd_q;    g.o_tnd_q[off] = oi.tnd_q;
+      f.o_tnd_qi[off] = o.tnd_qi;  g.o_tnd_qi[off] = oi.tnd_qi;
+      f.o_tnd_ql[off] = o.tnd_ql;  g.o_tnd_ql[off] = oi.tnd_ql;
+      f.o_tnd_t[off] = o.tnd_t;    g.o_tnd_t[off] = oi.tnd_t;
+      f.fplsl[offn] = c.rfl;            g.fplsl[offn] = ci.rfl;
+      f.fplsn[offn] = c.sfl;            g.fplsn[offn] = ci.sfl;
+      f.fhpsl[offn] = -c.rfl * p.RLVTT; g.fhpsl[offn] = -ci.rfl * p.RLVTT;
+      f.fhpsn[offn] = -c.sfl * p.RLSTT; g.fhpsn[offn] = -ci.sfl * p.RLSTT;
+    }
+    aph0 = in.aph1;
+    aph0_i = d.aph1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// AD backward.  Streams: [0,16) NL inputs with aph read at level k (not k+1), then the level-entry
+// fluxes fplsl/fplsn[k] written by the forward sweep, the 5 full-level seeds at k and the 4 flux
+// seeds at half level k+1.  The consumed seeds are zeroed by the launcher after the kernel
+// (cudaMemsetAsync on the same stream): a store to an address whose load is still in flight
+// serialises in L2 and made the first version of this kernel 3x slower (profiles/r1c).
+// ---------------------------------------------------------------------------------------
+enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_FPLSL, B_S_FHPSL, B_S_FPLSN, B_S_FHPSN, B_N };
+
+template <class R>
+inline Streams<R, B_N> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int64_t S) {
+  Streams<R, B_N> o;
+  const Streams<R, I_NL> a = nl_streams(f, S);
+  for (int n = 0; n < I_NL; ++n) o.p[n] = a.p[n];
+  o.p[I_APH1] = f.aph;  // backward sweep: the new value per level is aph[k]; aph[k+1] is carried
+  o.p[B_FPLSL] = f.fplsl; o.p[B_FPLSN] = f.fplsn;
+  o.p[B_S_TT] = s.tnd_t; o.p[B_S_TQ] = s.tnd_q; o.p[B_S_TQL] = s.tnd_ql; o.p[B_S_TQI] = s.tnd_qi; o.p[B_S_CLC] = s.clc;
+  o.p[B_S_FPLSL] = s.fplsl + S; o.p[B_S_FHPSL] = s.fhpsl + S; o.p[B_S_FPLSN] = s.fplsn + S; o.p[B_S_FHPSN] = s.fhpsn + S;
+  return o;
+}
+
+template <class R, int BLOCK>
+__device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                                  const ADOut<R>& a, const Streams<R, B_N>& in_s, Ring<R, B_N, BLOCK>& ring,
+                                                  const int32_t* jsel_in, uint32_t S, int nlev, uint32_t i, bool valid) {
+  using C = Cfg<false, true>;
+  const bool ad_ref = !p.ad_tl_predicates;
+  ring_issue(ring, in_s, (nlev - 1) & 1, uint32_t(nlev - 1) * S + i);
+  const int jsel = jsel_in[i];
+  const int ncand = tab.nw + 1;
+  const R aph_s = f.aph[uint32_t(nlev) * S + i];
+  const int t = threadIdx.x;
+
+  R a_rfl = R(0), a_sfl = R(0);  // adjoint of the fluxes entering the level below
+  R a_dp_below = R(0);           // a_dp of level k+1 (tmp_aph_s_i = 0 without the evaporation branch)
+  R aph1 = aph_s;
+  for (int k = nlev - 1; k >= 0; --k) {
+    const uint32_t off = uint32_t(k) * S + i;
+    const int st = k & 1;
+    cp_async_wait_all();
+    LevelIn<R> in;
+    ring_read_level(ring, st, 0, R(0), in);
+    in.aph0 = in.aph1;  // stream I_APH1 carries aph[k] in this sweep
+    in.aph1 = aph1;
+    Carry<R> c;
+    c.rfl = ring.v[st][B_FPLSL][t];
+    c.sfl = ring.v[st][B_FPLSN][t];
+    c.covptot = R(0);  // only feeds the (disabled) evaporation branch
+    LevelOut<R> so;
+    so.tnd_t = ring.v[st][B_S_TT][t];
+    so.tnd_q = ring.v[st][B_S_TQ][t];
+    so.tnd_ql = ring.v[st][B_S_TQL][t];
+    so.tnd_qi = ring.v[st][B_S_TQI][t];
+    so.clc = ring.v[st][B_S_CLC][t];
+    so.covptot = R(0);
+    // flux seeds at half level k+1 with the enthalpy-flux seeds folded in (AD :479-484,500-501)
+    R a_rfln = a_rfl + (ring.v[st][B_S_FPLSL][t] - ring.v[st][B_S_FHPSL][t] * p.RLVTT);
+    R a_sfln = a_sfl + (ring.v[st][B_S_FPLSN][t] - ring.v[st][B_S_FHPSN][t] * p.RLSTT);
+    if (k > 0) ring_issue(ring, in_s, (k - 1) & 1, off - S);
+
+    LevelOut<R> o;
+    Traj<R> tr;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    LevelIn<R> ad;
+    level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
+    a_rfl = a_rfln;
+    a_sfl = a_sfln;
+
+    if (valid) {
+      const uint32_t offn = off + S;
+      a.t[off] = ad.t;           a.tnd_t[off] = ad.tnd_t;
+      a.q[off] = ad.q;           a.tnd_q[off] = ad.tnd_q;
+      a.ql[off] = ad.ql;         a.tnd_ql[off] = ad.tnd_ql;
+      a.qi[off] = ad.qi;         a.tnd_qi[off] = ad.tnd_qi;
+      a.supsat[off] = ad.supsat; a.qsat[off] = ad.qsat;
+      a.ap[off] = ad.ap;         a.lude[off] = ad.lude;
+      a.mfu[off] = ad.mfu;       a.mfd[off] = ad.mfd;
+      // staggered fields (AD :969-986): aph_i[k+1] = a_dp(k) - a_dp(k+1); lu_i[k+1] = adjoint of lu[k+1]
+      a.aph[offn] = ad.aph1 - a_dp_below;
+      a.lu[offn] = ad.lu1;
+    }
+    a_dp_below = ad.aph1;
+    aph1 = in.aph0;
+  }
+  if (valid) {
+    a.aph[i] = -a_dp_below;
+    a.lu[i] = R(0);
+  }
+}
+
+}  // namespace cs2

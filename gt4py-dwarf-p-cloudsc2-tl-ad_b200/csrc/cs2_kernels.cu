@@ -14,7 +14,7 @@
 #include <cstring>
 #include <string>
 
-#include "cs2_columns.cuh"
+#include "cs2_device_columns.cuh"
 
 namespace {
 
@@ -36,6 +36,8 @@ int check_dims(const cs2_dims* d) {
   if (d->ncol < 0 || d->nlev < 1 || d->nlev > 4096) return fail(CS2_ERR_BAD_DIMS, "ncol < 0 or nlev outside [1, 4096]");
   if (d->ncol_stride < d->ncol) return fail(CS2_ERR_BAD_DIMS, "ncol_stride < ncol");
   if (d->ncol_stride % 32 != 0) return fail(CS2_ERR_MISALIGNED, "ncol_stride must be a multiple of 32 elements");
+  if (uint64_t(d->ncol_stride) * uint64_t(d->nlev + 1) >= (uint64_t(1) << 32))
+    return fail(CS2_ERR_BAD_DIMS, "ncol_stride * (nlev + 1) must be < 2^32 elements per call (kernels use 32-bit element offsets)");
   return CS2_OK;
 }
 
@@ -56,7 +58,7 @@ int check_nl_fields(const cs2_nl_fields* f, const char* what) {
   return check_ptrs(reinterpret_cast<const void* const*>(f), 26, what);
 }
 
-constexpr int kColumnBlock = 128;
+constexpr int kColumnBlock = 64;  // 65 536 columns = 1024 CTAs: one wave at 7 CTAs/SM (<= 144 registers)
 constexpr int kPointBlock = 256;
 
 // ---------------------------------------------------------------------------------------
@@ -110,37 +112,43 @@ perturbed_state_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int64_t nc
 }
 
 template <class R, class C>
-__global__ void __launch_bounds__(kColumnBlock)
+__global__ void __launch_bounds__(kColumnBlock, 7)
 nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
-          const __grid_constant__ cs2::NLFields<R> f, int64_t ncol, int64_t S, int nlev, int ad_ref,
-          int32_t* jsel_out) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= ncol) return;
+          const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
+          int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out) {
+  __shared__ cs2::Ring<R, cs2::I_NL, kColumnBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;  // out-of-range threads shadow the last column and store nothing
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::column_nl<R, C>(p, tab, f, S, nlev, i, ad_ref != 0, jsel_out);
+  cs2::dev_column_nl<R, C, kColumnBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0, jsel_out);
 }
 
 template <class R>
 __global__ void __launch_bounds__(kColumnBlock)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
-          const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g, int64_t ncol,
-          int64_t S, int nlev) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= ncol) return;
+          const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
+          const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
+  __shared__ cs2::Ring<R, 2 * cs2::I_NL, kColumnBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::column_tl<R>(p, tab, f, g, S, nlev, i);
+  cs2::dev_column_tl<R, kColumnBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 template <class R>
 __global__ void __launch_bounds__(kColumnBlock)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
-              const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADSeeds<R> s,
-              const __grid_constant__ cs2::ADOut<R> a, const int32_t* __restrict__ jsel, int64_t ncol, int64_t S,
-              int nlev) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= ncol) return;
+              const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
+              const __grid_constant__ cs2::Streams<R, cs2::B_N> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
+              int64_t S, int nlev) {
+  __shared__ cs2::Ring<R, cs2::B_N, kColumnBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::column_ad_bwd<R>(p, tab, f, s, a, jsel, S, nlev, i);
+  cs2::dev_column_ad_bwd<R, kColumnBlock>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 // ---- reductions -----------------------------------------------------------------------
@@ -316,11 +324,12 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   if (d->ncol == 0) return CS2_OK;
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
+  const cs2::Streams<R, cs2::I_NL> ns = cs2::nl_streams<R>(nf, d->ncol_stride);
   const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
   const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
   const bool tetens = P->LPHYLIN || P->LDRAIN1D;
 #define CS2_LAUNCH_NL(E, T)                                                                                  \
-  nl_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, d->ncol, d->ncol_stride, d->nlev, \
+  nl_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev, \
                                                               ad_ref ? 1 : 0, jsel_out)
   if (evap && tetens) CS2_LAUNCH_NL(true, true);
   else if (evap) CS2_LAUNCH_NL(true, false);
@@ -366,9 +375,21 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   a.tnd_q = static_cast<R*>(adj->out_tnd_cml_q_i); a.tnd_ql = static_cast<R*>(adj->out_tnd_cml_ql_i);
   a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
   const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
-  ad_bwd_kernel<R><<<grid, kColumnBlock, 0, st>>>(cs2::make_dev_params<R>(*P, dt), tables, cs2::make_nl_fields<R>(*traj),
-                                                 s, a, jsel, d->ncol, d->ncol_stride, d->nlev);
-  return check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch");
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*traj);
+  ad_bwd_kernel<R><<<grid, kColumnBlock, 0, st>>>(cs2::make_dev_params<R>(*P, dt), tables, nf, a,
+                                                 cs2::ad_streams<R>(nf, s, d->ncol_stride), jsel, d->ncol, d->ncol_stride,
+                                                 d->nlev);
+  if (int rc = check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch")) return rc;
+  // the reference stencil consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984)
+  const size_t full = size_t(d->nlev) * size_t(d->ncol_stride) * sizeof(R);
+  const size_t half = size_t(d->nlev + 1) * size_t(d->ncol_stride) * sizeof(R);
+  R* const full_seeds[6] = {s.tnd_t, s.tnd_q, s.tnd_ql, s.tnd_qi, s.clc, s.covptot};
+  R* const half_seeds[4] = {s.fhpsl, s.fhpsn, s.fplsl, s.fplsn};
+  for (R* ptr : full_seeds)
+    if (int rc = check_cuda(cudaMemsetAsync(ptr, 0, full, st), "cloudsc2_ad seed reset")) return rc;
+  for (R* ptr : half_seeds)
+    if (int rc = check_cuda(cudaMemsetAsync(ptr, 0, half, st), "cloudsc2_ad seed reset")) return rc;
+  return CS2_OK;
 }
 }  // namespace
 
@@ -466,13 +487,15 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
   if (dims->ncol == 0) return CS2_OK;
   const unsigned grid = (unsigned)((dims->ncol + kColumnBlock - 1) / kColumnBlock);
   if (dims->dtype == CS2_F64) {
+    const auto f = cs2::make_nl_fields<double>(*traj), g = cs2::make_nl_fields<double>(*pert);
     tl_kernel<double><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<double>(*params, dt), level_tables_dev, cs2::make_nl_fields<double>(*traj),
-        cs2::make_nl_fields<double>(*pert), dims->ncol, dims->ncol_stride, dims->nlev);
+        cs2::make_dev_params<double>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<double>(f, g, dims->ncol_stride),
+        dims->ncol, dims->ncol_stride, dims->nlev);
   } else {
+    const auto f = cs2::make_nl_fields<float>(*traj), g = cs2::make_nl_fields<float>(*pert);
     tl_kernel<float><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<float>(*params, dt), level_tables_dev, cs2::make_nl_fields<float>(*traj),
-        cs2::make_nl_fields<float>(*pert), dims->ncol, dims->ncol_stride, dims->nlev);
+        cs2::make_dev_params<float>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<float>(f, g, dims->ncol_stride),
+        dims->ncol, dims->ncol_stride, dims->nlev);
   }
   return check_cuda(cudaGetLastError(), "cloudsc2_tl launch");
 }

@@ -59,7 +59,7 @@ struct AdjStep {
 template <class R>
 struct Traj {
   R t0, q0, ql0, qi0, dp, rdp, rap;
-  R zzinv, lfdcp, lsdcp, lvdcp;
+  R zzinv, lfdcp, lsdcp, lvdcp, rlfdcp;
   bool cold, ice, clip_esdp;
   R th, fwat, z3es, z4es, rtw, rti, rtm4, foeew, facw, faci, fac, cor, dqsdtemp, corqs, qlim;
   R scalm, crh2, supsat, qsat, qcrit, qt;
@@ -210,11 +210,13 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
     tr.lfdcp = p.lfdcp0;
     tr.lsdcp = p.lsdcp0;
     tr.lvdcp = p.lvdcp0;
+    tr.rlfdcp = p.rlfdcp0;
   } else {
     tr.zzinv = rcp(p.RCPD + p.RCPD * p.RVTMP2 * tr.q0);
     tr.lfdcp = p.RLMLT * tr.zzinv;
     tr.lsdcp = p.RLSTT * tr.zzinv;
     tr.lvdcp = p.RLVTT * tr.zzinv;
+    tr.rlfdcp = rcp(tr.lfdcp);
   }
 
   // dqs/dT correction factor (:141-160)
@@ -338,7 +340,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   tr.cons = tr.rcons = tr.snmlt = zero;
   tr.allm = tr.warm2 = false;
   if (tr.melt) {
-    tr.cons = p.cons2 * tr.dp / tr.lfdcp;
+    tr.cons = p.cons2 * tr.dp * tr.rlfdcp;
     tr.rcons = tr.lfdcp * p.rgdt * tr.rdp;
     tr.warm2 = t0 > p.meltp2;
     const R z2s = tr.warm2 ? tr.cons * (t0 - p.meltp2) : zero;
@@ -410,13 +412,16 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   }
 
   // first-guess T and q (:328-344)
-  const R ludeg = in.lude * tr.gdp;
-  const R dqdt = -(tr.condl1 + tr.condi1) + (in.lude + tr.evapr + tr.evaps) * tr.gdp;
-  const R dtdt = tr.lvdcp * tr.condl1 + tr.lsdcp * tr.condi1 -
-                 (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps + in.lude * tr.ldcp -
-                  (tr.lsdcp - tr.lvdcp) * tr.rfreeze1) *
-                     tr.gdp;
-  (void)ludeg;
+  R dqdt, dtdt;
+  if (C::EVAP) {
+    dqdt = -(tr.condl1 + tr.condi1) + (in.lude + tr.evapr + tr.evaps) * tr.gdp;
+    dtdt = tr.lvdcp * tr.condl1 + tr.lsdcp * tr.condi1 -
+           (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps + in.lude * tr.ldcp - (tr.lsdcp - tr.lvdcp) * tr.rfreeze1) * tr.gdp;
+  } else {
+    dqdt = -(tr.condl1 + tr.condi1) + in.lude * tr.gdp;
+    dtdt = tr.lvdcp * tr.condl1 + tr.lsdcp * tr.condi1 -
+           (in.lude * tr.ldcp - (tr.lsdcp - tr.lvdcp) * tr.rfreeze1) * tr.gdp;
+  }
   tr.t3 = tr.tmelt + p.dt * dtdt;
   tr.qa = tr.q0 + p.dt * dqdt;
 
@@ -451,10 +456,16 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
 
   // outputs (:367-388)
   o.clc = tr.clc_o;
-  o.tnd_q = -(tr.condl2 + tr.condi2) + (in.lude + tr.evapr + tr.evaps) * tr.gdp;
-  o.tnd_t = tr.lvdcp * tr.condl2 + tr.lsdcp * tr.condi2 -
-            (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps + in.lude * tr.ldcp - (tr.lsdcp - tr.lvdcp) * tr.rfreeze3) *
-                tr.gdp;
+  if (C::EVAP) {
+    o.tnd_q = -(tr.condl2 + tr.condi2) + (in.lude + tr.evapr + tr.evaps) * tr.gdp;
+    o.tnd_t = tr.lvdcp * tr.condl2 + tr.lsdcp * tr.condi2 -
+              (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps + in.lude * tr.ldcp - (tr.lsdcp - tr.lvdcp) * tr.rfreeze3) *
+                  tr.gdp;
+  } else {
+    o.tnd_q = -(tr.condl2 + tr.condi2) + in.lude * tr.gdp;
+    o.tnd_t = tr.lvdcp * tr.condl2 + tr.lsdcp * tr.condi2 -
+              (in.lude * tr.ldcp - (tr.lsdcp - tr.lvdcp) * tr.rfreeze3) * tr.gdp;
+  }
   o.tnd_ql = (tr.qlwc - tr.ql0) * p.rdt;
   o.tnd_qi = (tr.qiwc - tr.qi0) * p.rdt;
   c.rfl = rfln;
@@ -510,11 +521,11 @@ CS2_HD void level_tl(const DevParams<R>& p, const LevelIn<R>& in, const LevelIn<
     const R qpd_i = qsat_i - qt_i;
     const R qcd_i = qsat_i - qcrit_i;
     const R den = tr.qcd - scalm * (tr.qt - tr.qcrit);
-    clc_i = R(-0.5) / tr.tmp3 * (qpd_i * den - tr.qpd * (qcd_i - scalm * (qt_i - qcrit_i))) * tr.rden * tr.rden;
+    clc_i = R(-0.5) * rcp(tr.tmp3) * (qpd_i * den - tr.qpd * (qcd_i - scalm * (qt_i - qcrit_i))) * tr.rden * tr.rden;
     if (p.lregcl) {
-      const R rat = tr.qpd / tr.qcd;
+      const R rat = tr.qpd * rcp(tr.qcd);
       const R u = one - scalm * (one - rat);
-      const R yyy = min_(R(0.3), R(3.5) * sqrt_(rat * (u * u * u)) / (one - scalm));
+      const R yyy = min_(R(0.3), R(3.5) * sqrt_(rat * (u * u * u)) * rcp(one - scalm));
       clc_i *= yyy;
     }
     const R wq = scalm * tr.qpd + (one - scalm) * tr.qcd;
@@ -560,7 +571,7 @@ CS2_HD void level_tl(const DevParams<R>& p, const LevelIn<R>& in, const LevelIn<
   // melting (TL :399-427)
   R rfln_i = ci.rfl, sfln_i = ci.sfl;
   if (tr.melt) {
-    const R cons_i = tr.cons * (dp_i * tr.rdp - lfdcp_i / tr.lfdcp);
+    const R cons_i = tr.cons * (dp_i * tr.rdp - lfdcp_i * tr.rlfdcp);
     const R z2s_i = tr.warm2 ? cons_i * (tr.t0 - p.meltp2) + tr.cons * t_i : zero;
     const R snmlt_i = tr.allm ? ci.sfl : z2s_i;
     rfln_i = ci.rfl + snmlt_i;
@@ -771,7 +782,7 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
       a_cons += (tr.t0 - p.meltp2) * a_z2s;
     }
     a_dp += tr.cons * tr.rdp * a_cons;
-    a_lfdcp = -tr.cons / tr.lfdcp * a_cons;
+    a_lfdcp = -tr.cons * tr.rlfdcp * a_cons;
   }
   a_rfln = a_rfl;
   a_sfln = a_sfl;
@@ -829,11 +840,11 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
     R a_qcd = (one - scalm) * a_qc1 * (tr.clc * tr.clc);
     a_clc += R(2) * (scalm * tr.qpd + (one - scalm) * tr.qcd) * tr.clc * a_qc1;
     if (p.lregcl) {
-      const R rat = tr.qpd / tr.qcd;
+      const R rat = tr.qpd * rcp(tr.qcd);
       const R u = one - scalm * (one - rat);
-      a_clc *= min_(R(0.3), R(3.5) * sqrt_(rat * (u * u * u)) / (one - scalm));
+      a_clc *= min_(R(0.3), R(3.5) * sqrt_(rat * (u * u * u)) * rcp(one - scalm));
     }
-    const R h = R(0.5) / tr.tmp3 * a_clc * tr.rden;
+    const R h = R(0.5) * rcp(tr.tmp3) * a_clc * tr.rden;
     a_qpd -= h;
     const R a_den = h * tr.qpd * tr.rden;
     a_qcd += a_den;
