@@ -189,8 +189,10 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
 // AD backward.  Streams: [0,16) NL inputs with aph read at level k (not k+1), then the level-entry
 // fluxes fplsl/fplsn[k] written by the forward sweep, the 5 full-level seeds at k and the 4 flux
 // seeds at half level k+1.  The consumed seeds are zeroed by the launcher after the kernel
-// (cudaMemsetAsync on the same stream): a store to an address whose load is still in flight
-// serialises in L2 and made the first version of this kernel 3x slower (profiles/r1c).
+// (cudaMemsetAsync on the same stream).  Measured alternatives: zeroing in the kernel right after the
+// load (first version) serialises store-after-load on the same address in L2 and made the kernel 4x
+// slower (profiles/r1c_ad_bwd.md); zeroing in the kernel one level after the copy completed is correct
+// but still 2-5 % slower than the separate memsets (10 more stores per level in a latency-bound loop).
 // ---------------------------------------------------------------------------------------
 enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_FPLSL, B_S_FHPSL, B_S_FPLSN, B_S_FHPSN, B_N };
 

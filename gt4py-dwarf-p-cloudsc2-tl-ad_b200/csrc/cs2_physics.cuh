@@ -61,7 +61,7 @@ struct Traj {
   R t0, q0, ql0, qi0, dp, rdp, rap;
   R zzinv, lfdcp, lsdcp, lvdcp, rlfdcp;
   bool cold, ice, clip_esdp;
-  R th, fwat, z3es, z4es, rtw, rti, rtm4, foeew, facw, faci, fac, cor, dqsdtemp, corqs, qlim;
+  R tp1, fwat, z3es, z4es, rtw, rti, rtm4, foeew, facw, faci, fac, cor, dqsdtemp, corqs, qlim;
   R scalm, crh2, supsat, qsat, qcrit, qt;
   int branch;  // 0: qt < qcrit, 1: qt >= qsat, 2: partial cloud
   R qpd, qcd, rden, tmp3, clc, qc1;
@@ -226,13 +226,13 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   R esdp;
   if (C::TETENS) {
     if (tr.cold) {
-      tr.th = tanh_(R(0.17) * (t0 - p.RLPTRC));
-      tr.fwat = R(0.545) * (tr.th + one);
+      tr.tp1 = one_plus_tanh<R>(R(0.17) * (t0 - p.RLPTRC));
+      tr.fwat = R(0.545) * tr.tp1;
       tr.z3es = p.R3IES;
       tr.z4es = p.R4IES;
       tr.rtm4 = tr.rti;
     } else {
-      tr.th = one;
+      tr.tp1 = R(2);
       tr.fwat = one;
       tr.z3es = p.R3LES;
       tr.z4es = p.R4LES;
@@ -243,7 +243,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
     tr.clip_esdp = esdp1 > p.ZQMAX;
     esdp = tr.clip_esdp ? p.ZQMAX : esdp1;
   } else {
-    tr.th = one;
+    tr.tp1 = R(2);
     tr.fwat = foealfa(p, t0);
     tr.foeew = foeew_mixed(p, t0, tr.fwat);
     tr.z3es = p.R3LES;
@@ -497,7 +497,7 @@ CS2_HD void level_tl(const DevParams<R>& p, const LevelIn<R>& in, const LevelIn<
   }
 
   // dqs/dT correction factor (TL :188-222)
-  const R fwat_i = tr.cold ? R(0.545) * R(0.17) * t_i * ((one - tr.th) * (one + tr.th)) : zero;
+  const R fwat_i = tr.cold ? R(0.545) * R(0.17) * t_i * (tr.tp1 * (R(2) - tr.tp1)) : zero;
   const R foeew_i = tr.z3es * (p.RTT - tr.z4es) * t_i * tr.foeew * tr.rtm4 * tr.rtm4;
   R esdp_i = foeew_i * tr.rap - tr.foeew * d.ap * tr.rap * tr.rap;
   if (tr.clip_esdp) esdp_i = zero;
@@ -873,7 +873,7 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_foeew += a_esdp * tr.rap;
   a_ap -= a_esdp * tr.foeew * tr.rap * tr.rap;
   a_t0 += tr.z3es * (p.RTT - tr.z4es) * a_foeew * tr.foeew * tr.rtm4 * tr.rtm4;
-  if (tr.cold) a_t0 += R(0.545) * R(0.17) * a_fwat * ((one - tr.th) * (one + tr.th));
+  if (tr.cold) a_t0 += R(0.545) * R(0.17) * a_fwat * (tr.tp1 * (R(2) - tr.tp1));
 
   // ---- latent-heat ratios (AD :988-991)
   if (!p.rvtmp2_zero) {
