@@ -206,3 +206,38 @@ def test_reductions_match_numpy():
         n = symmetry_norms(flds[:3], flds[3:]).cpu().numpy()
         refn = sum(np.sum(arrs[i].astype(np.float64) * arrs[i + 3], axis=0) for i in range(3))
         np.testing.assert_allclose(n, refn, rtol=1e-9, atol=1e-9)
+
+
+def test_drivers_run_end_to_end(tmp_path):
+    """The three reference-style drivers (drivers/run_*.py) on synthetic inputs."""
+    import subprocess
+    import sys
+
+    csv_path = tmp_path / "perf.csv"
+    for mod, extra in (("drivers.run_nonlinear", ["--num-cols", "300", "--num-runs", "2", "--output-csv-file", str(csv_path)]),
+                       ("drivers.run_taylor_test", ["--num-cols", "300"]),
+                       ("drivers.run_symmetry_test", ["--num-cols", "300"])):
+        res = subprocess.run([sys.executable, "-m", mod, *extra], cwd=H.ROOT, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        if mod.endswith("nonlinear"):
+            assert "validation passed" in res.stdout
+        if mod.endswith("taylor_test"):
+            assert "The test passed with penalty" in res.stdout
+        if mod.endswith("symmetry_test"):
+            assert "The symmetry test passed. HOORAY!" in res.stdout
+    assert csv_path.read_text().count("nl-b200") == 1
+
+
+def test_multi_gpu_sharded_taylor_and_symmetry():
+    """N>1 on real GPUs (NCCL): sharded Taylor / symmetry equal the single-GPU run (tests/dist_gpu_worker.py)."""
+    import subprocess
+    import sys
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr",
+         "127.0.0.1", "--master-port", "29533", os.path.join(H.ROOT, "tests", "dist_gpu_worker.py"), "--columns", "4000"],
+        capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "DIST_GPU_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
