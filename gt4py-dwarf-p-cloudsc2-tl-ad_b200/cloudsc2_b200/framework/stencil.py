@@ -249,7 +249,11 @@ class Cloudsc2ADStencil(StencilObject):
 
     def __init__(self, externals: Dict[str, Any], gt4py_config: Any = None) -> None:
         super().__init__(externals, gt4py_config)
-        self.mode = _lib.CS2_AD_RECOMPUTE
+        # trajectory handling of the backward sweep: "recompute" (default) or "checkpoint"
+        mode = str(externals.get("AD_TRAJECTORY", "recompute"))
+        if mode not in ("recompute", "checkpoint"):
+            raise ValueError("AD_TRAJECTORY must be 'recompute' or 'checkpoint'")
+        self.mode = _lib.CS2_AD_CHECKPOINT if mode == "checkpoint" else _lib.CS2_AD_RECOMPUTE
         self._workspace: Optional[torch.Tensor] = None
 
     def __call__(self, *, in_eta, dt, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None, **fields):

@@ -39,7 +39,7 @@ AD_DIAG_ADJOINTS = ("aph", "ap", "q", "qsat", "t", "ql", "qi", "lude", "lu", "mf
 class Cloudsc2AD(ImplicitTendencyComponent):
     def __init__(self, computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params,
                  yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
-                 ad_predicates=None):
+                 ad_predicates=None, ad_trajectory=None):
         super().__init__(computational_grid, enable_checks=enable_checks, gt4py_config=gt4py_config)
         nk = self.computational_grid.grids[I, J, K].shape[2]
         self.klevel = gt_zeros(self.computational_grid, (K,), gt4py_config=self.gt4py_config, dtype_name="int")
@@ -48,9 +48,12 @@ class Cloudsc2AD(ImplicitTendencyComponent):
         if ad_predicates not in ("tl", "reference"):
             raise ValueError("ad_predicates must be 'tl' or 'reference'")
         self.ad_predicates = ad_predicates
+        # "recompute": the backward sweep recomputes each level's trajectory; "checkpoint": the forward sweep
+        # stores the 9 transcendental results per point to an HBM workspace and the backward sweep replays them
+        self.ad_trajectory = ad_trajectory or os.environ.get("CS2_AD_TRAJECTORY", "recompute")
         externals = physics_externals(lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params, yrephli_params,
                                       yrncl_params, yrphnc_params, NLEV=nk,
-                                      AD_TL_PREDICATES=(ad_predicates == "tl"))
+                                      AD_TL_PREDICATES=(ad_predicates == "tl"), AD_TRAJECTORY=self.ad_trajectory)
         self.cloudsc2 = self.compile_stencil("cloudsc2_ad", externals)
 
     @cached_property

@@ -27,7 +27,7 @@ AD_DIAGS = ("f_ap_i", "f_aph_i", "f_t_i", "f_q_i", "f_qsat_i", "f_ql_i", "f_qi_i
 class SymmetryTest:
     def __init__(self, computational_grid, factor, kflag, lphylin, ldrain1d, yoethf_params, yomcst_params,
                  yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
-                 ad_predicates=None):
+                 ad_predicates=None, ad_trajectory=None):
         self.f = factor
         kw = dict(enable_checks=enable_checks, gt4py_config=gt4py_config)
         self.saturation = Saturation(computational_grid, kflag, lphylin, yoethf_params, yomcst_params, **kw)
@@ -35,7 +35,7 @@ class SymmetryTest:
                                       yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, **kw)
         self.cloudsc2_ad = Cloudsc2AD(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
                                       yrecldp_params, yrephli_params, yrncl_params, yrphnc_params,
-                                      ad_predicates=ad_predicates, **kw)
+                                      ad_predicates=ad_predicates, ad_trajectory=ad_trajectory, **kw)
         self.state_increment = StateIncrement(computational_grid, factor, ignore_supsat=True, **kw)
         self.diags_sat: Dict[str, Any] = {}
         self.state_i: Dict[str, Any] = {}

@@ -114,7 +114,8 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     load_level(f, S, i, k, aph0, in);
     LevelOut<R> o;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    Trans<R, 0> x;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     f.clc[off] = o.clc;
     f.covptot[off] = o.covptot;
@@ -154,7 +155,8 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     load_level(g, S, i, k, aph0_i, d);
     LevelOut<R> o, oi;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr);
+    Trans<R, 0> x;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     const uint32_t offn = off + uint32_t(S);
@@ -204,7 +206,8 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     c.covptot = R(0);  // only feeds the (disabled) evaporation branch
     LevelOut<R> o;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    Trans<R, 0> x;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
 
     // seeds: tendencies / cloud cover at k, fluxes at half level k+1 with the enthalpy-flux
     // seeds folded in (AD :479-484,500-501); all consumed seeds are zeroed like the reference.

@@ -79,10 +79,11 @@ __device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, i
 // ---------------------------------------------------------------------------------------
 // NL (and AD forward when jsel_out != nullptr)
 // ---------------------------------------------------------------------------------------
-template <class R, class C, int BLOCK>
+// CKPT: also record the level's transcendental results into `ck` ([CK_N][nlev][S], CS2_AD_CHECKPOINT).
+template <class R, class C, int BLOCK, bool CKPT>
 __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const Streams<R, I_NL>& in_s, Ring<R, I_NL, BLOCK>& ring, uint32_t S,
-                                              int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out) {
+                                              int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out, R* ck) {
   ring_issue(ring, in_s, 0, i);  // level 0 is in flight while the tropopause scan runs
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   if (jsel_out && valid) jsel_out[i] = jsel;
@@ -107,7 +108,14 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
     LevelOut<R> o;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    Trans<R, CKPT ? 1 : 0> x;
+    if (CKPT) x.defaults();
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
+    if (CKPT && valid) {
+      const uint32_t plane = uint32_t(nlev) * S;
+#pragma unroll
+      for (int n = 0; n < CK_N; ++n) ck[uint32_t(n) * plane + off] = x.v[n];
+    }
     if (valid) {
       f.clc[off] = o.clc;
       f.covptot[off] = o.covptot;
@@ -165,7 +173,8 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
     LevelOut<R> o, oi;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr);
+    Trans<R, 0> x;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
     if (valid) {
       const uint32_t offn = off + S;
@@ -194,11 +203,16 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
 // slower (profiles/r1c_ad_bwd.md); zeroing in the kernel one level after the copy completed is correct
 // but still 2-5 % slower than the separate memsets (10 more stores per level in a latency-bound loop).
 // ---------------------------------------------------------------------------------------
-enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_FPLSL, B_S_FHPSL, B_S_FPLSN, B_S_FHPSN, B_N };
+enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_FPLSL, B_S_FHPSL, B_S_FPLSN, B_S_FHPSN, B_N,
+       B_CK = B_N, B_NCK = B_N + CK_N };
 
-template <class R>
-inline Streams<R, B_N> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int64_t S) {
-  Streams<R, B_N> o;
+// NS = B_N (recompute) or B_NCK (checkpoint: CK_N more streams with the recorded transcendentals)
+template <class R, int NS>
+inline Streams<R, NS> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int64_t S, int nlev, const R* ck) {
+  Streams<R, NS> o;
+  if constexpr (NS > B_N) {
+    for (int n = 0; n < CK_N; ++n) o.p[B_N + n] = ck + size_t(n) * size_t(nlev) * size_t(S);
+  }
   const Streams<R, I_NL> a = nl_streams(f, S);
   for (int n = 0; n < I_NL; ++n) o.p[n] = a.p[n];
   o.p[I_APH1] = f.aph;  // backward sweep: the new value per level is aph[k]; aph[k+1] is carried
@@ -208,10 +222,11 @@ inline Streams<R, B_N> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int
   return o;
 }
 
-template <class R, int BLOCK>
+template <class R, int BLOCK, int NS>
 __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
-                                                  const ADOut<R>& a, const Streams<R, B_N>& in_s, Ring<R, B_N, BLOCK>& ring,
+                                                  const ADOut<R>& a, const Streams<R, NS>& in_s, Ring<R, NS, BLOCK>& ring,
                                                   const int32_t* jsel_in, uint32_t S, int nlev, uint32_t i, bool valid) {
+  constexpr bool CKPT = NS > B_N;
   using C = Cfg<false, true>;
   const bool ad_ref = !p.ad_tl_predicates;
   ring_issue(ring, in_s, (nlev - 1) & 1, uint32_t(nlev - 1) * S + i);
@@ -245,11 +260,17 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     // flux seeds at half level k+1 with the enthalpy-flux seeds folded in (AD :479-484,500-501)
     R a_rfln = a_rfl + (ring.v[st][B_S_FPLSL][t] - ring.v[st][B_S_FHPSL][t] * p.RLVTT);
     R a_sfln = a_sfl + (ring.v[st][B_S_FPLSN][t] - ring.v[st][B_S_FHPSN][t] * p.RLSTT);
+
+    Trans<R, CKPT ? 2 : 0> x;
+    if constexpr (CKPT) {
+#pragma unroll
+      for (int n = 0; n < CK_N; ++n) x.v[n] = ring.v[st][B_N + n][t];
+    }
     if (k > 0) ring_issue(ring, in_s, (k - 1) & 1, off - S);
 
     LevelOut<R> o;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr);
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     LevelIn<R> ad;
     level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
     a_rfl = a_rfln;

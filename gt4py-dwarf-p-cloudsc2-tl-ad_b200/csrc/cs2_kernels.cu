@@ -111,17 +111,18 @@ perturbed_state_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int64_t nc
   for (int n = 0; n < CS2_NSTATE; ++n) f.out[n][off] = v[n] + fac * w[n];
 }
 
-template <class R, class C>
+template <class R, class C, bool CKPT>
 __global__ void __launch_bounds__(kColumnBlock, 7)
 nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
-          int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out) {
+          int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out, R* ck) {
   __shared__ cs2::Ring<R, cs2::I_NL, kColumnBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;  // out-of-range threads shadow the last column and store nothing
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_nl<R, C, kColumnBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0, jsel_out);
+  cs2::dev_column_nl<R, C, kColumnBlock, CKPT>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0,
+                                               jsel_out, ck);
 }
 
 template <class R>
@@ -137,18 +138,18 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
   cs2::dev_column_tl<R, kColumnBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
-template <class R>
+template <class R, int NS>
 __global__ void __launch_bounds__(kColumnBlock)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
-              const __grid_constant__ cs2::Streams<R, cs2::B_N> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
+              const __grid_constant__ cs2::Streams<R, NS> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
               int64_t S, int nlev) {
-  __shared__ cs2::Ring<R, cs2::B_N, kColumnBlock> ring;
+  __shared__ cs2::Ring<R, NS, kColumnBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_ad_bwd<R, kColumnBlock>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
+  cs2::dev_column_ad_bwd<R, kColumnBlock, NS>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 // ---- reductions -----------------------------------------------------------------------
@@ -320,7 +321,7 @@ int launch_state(const cs2_dims* d, double f, int mode, int ignore_supsat, const
 
 template <class R>
 int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
-              bool ad_ref, int32_t* jsel_out, cudaStream_t st) {
+              bool ad_ref, int32_t* jsel_out, R* ck, cudaStream_t st) {
   if (d->ncol == 0) return CS2_OK;
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
@@ -328,10 +329,13 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
   const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
   const bool tetens = P->LPHYLIN || P->LDRAIN1D;
-#define CS2_LAUNCH_NL(E, T)                                                                                  \
-  nl_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev, \
-                                                              ad_ref ? 1 : 0, jsel_out)
-  if (evap && tetens) CS2_LAUNCH_NL(true, true);
+#define CS2_LAUNCH_NL(E, T)                                                                                         \
+  nl_kernel<R, cs2::Cfg<E, T>, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev, \
+                                                                     ad_ref ? 1 : 0, jsel_out, nullptr)
+  if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
+    nl_kernel<R, cs2::Cfg<false, true>, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
+                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
+  else if (evap && tetens) CS2_LAUNCH_NL(true, true);
   else if (evap) CS2_LAUNCH_NL(true, false);
   else if (tetens) CS2_LAUNCH_NL(false, true);
   else CS2_LAUNCH_NL(false, false);
@@ -355,10 +359,13 @@ cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 namespace {
 template <class R>
 int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
-              const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, cudaStream_t st) {
+              const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, int mode, cudaStream_t st) {
   int32_t* jsel = static_cast<int32_t*>(ws);
+  R* ck = nullptr;
+  if (mode == CS2_AD_CHECKPOINT)
+    ck = reinterpret_cast<R*>(static_cast<char*>(ws) + ((size_t(d->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255)));
   const bool ad_ref = !P->AD_TL_PREDICATES;
-  if (int rc = launch_nl<R>(d, P, dt, tables, traj, ad_ref, jsel, st)) return rc;
+  if (int rc = launch_nl<R>(d, P, dt, tables, traj, ad_ref, jsel, ck, st)) return rc;
   if (d->ncol == 0) return CS2_OK;
   cs2::ADSeeds<R> s;
   s.tnd_t = static_cast<R*>(seeds->in_tnd_t_i); s.tnd_q = static_cast<R*>(seeds->in_tnd_q_i);
@@ -376,9 +383,14 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
   const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*traj);
-  ad_bwd_kernel<R><<<grid, kColumnBlock, 0, st>>>(cs2::make_dev_params<R>(*P, dt), tables, nf, a,
-                                                 cs2::ad_streams<R>(nf, s, d->ncol_stride), jsel, d->ncol, d->ncol_stride,
-                                                 d->nlev);
+  if (ck)
+    ad_bwd_kernel<R, cs2::B_NCK><<<grid, kColumnBlock, 0, st>>>(
+        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
+        jsel, d->ncol, d->ncol_stride, d->nlev);
+  else
+    ad_bwd_kernel<R, cs2::B_N><<<grid, kColumnBlock, 0, st>>>(
+        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
+        jsel, d->ncol, d->ncol_stride, d->nlev);
   if (int rc = check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch")) return rc;
   // the reference stencil consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984)
   const size_t full = size_t(d->nlev) * size_t(d->ncol_stride) * sizeof(R);
@@ -473,8 +485,8 @@ int cs2_nl(const cs2_dims* dims, const cs2_params* params, double dt, const void
   if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_nl: params or level tables NULL");
   if (int rc = check_nl_fields(f, "cloudsc2_nl fields")) return rc;
   return dims->dtype == CS2_F64
-             ? launch_nl<double>(dims, params, dt, level_tables_dev, f, false, nullptr, as_stream(stream))
-             : launch_nl<float>(dims, params, dt, level_tables_dev, f, false, nullptr, as_stream(stream));
+             ? launch_nl<double>(dims, params, dt, level_tables_dev, f, false, nullptr, nullptr, as_stream(stream))
+             : launch_nl<float>(dims, params, dt, level_tables_dev, f, false, nullptr, nullptr, as_stream(stream));
 }
 
 int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
@@ -503,8 +515,9 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
   (void)params;
   if (!dims || dims->ncol_stride <= 0) return 0;
-  size_t bytes = size_t(dims->ncol_stride) * sizeof(int32_t);  // tropopause candidate per column
-  (void)mode;
+  size_t bytes = (size_t(dims->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255);  // tropopause candidate per column
+  if (mode == CS2_AD_CHECKPOINT)  // CK_N transcendental results per (level, column)
+    bytes += size_t(cs2::CK_N) * size_t(dims->nlev) * size_t(dims->ncol_stride) * (dims->dtype == CS2_F32 ? 4 : 8);
   return (bytes + 255) & ~size_t(255);
 }
 
@@ -521,13 +534,11 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(adj), 16, "cloudsc2_ad adjoint outputs")) return rc;
   if (int rc = check_tl_ad_flags(params, "cloudsc2_ad")) return rc;
   if (mode != CS2_AD_RECOMPUTE && mode != CS2_AD_CHECKPOINT) return fail(CS2_ERR_BAD_DIMS, "cloudsc2_ad: unknown mode");
-  if (mode == CS2_AD_CHECKPOINT)
-    return fail(CS2_ERR_UNSUPPORTED, "cloudsc2_ad: CS2_AD_CHECKPOINT is not implemented yet; use CS2_AD_RECOMPUTE");
   if (!workspace_dev || workspace_bytes < cs2_ad_workspace_bytes(dims, params, mode))
     return fail(CS2_ERR_WORKSPACE, "cloudsc2_ad: workspace missing or too small");
   return dims->dtype == CS2_F64
-             ? launch_ad<double>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, as_stream(stream))
-             : launch_ad<float>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, as_stream(stream));
+             ? launch_ad<double>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream))
+             : launch_ad<float>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream));
 }
 
 static int taylor_blocks(const cs2_dims* dims) {

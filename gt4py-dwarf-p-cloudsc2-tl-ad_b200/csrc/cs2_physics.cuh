@@ -88,6 +88,33 @@ struct Traj {
   R dq, dr2, rfreeze3, condl2, condi2;
 };
 
+// Transcendental results of a level (the expensive part of the trajectory).  MODE 0: compute;
+// MODE 1: compute and record (AD forward sweep, CS2_AD_CHECKPOINT); MODE 2: replay recorded values
+// (AD backward sweep, CS2_AD_CHECKPOINT) -- the cheap algebra around them is always recomputed.
+enum { CK_TP1, CK_FOEEW, CK_LTMP1, CK_LTMP2, CK_ITMP11, CK_ITMP12, CK_ITMP2, CK_SB, CK_SA, CK_N };
+
+template <class R, int MODE>
+struct Trans {
+  R v[CK_N];
+  CS2_HD void defaults() {
+    v[CK_TP1] = R(2);
+#pragma unroll
+    for (int n = 1; n < CK_N; ++n) v[n] = R(1);
+  }
+  CS2_HD R exp(int idx, R x) {
+    if (MODE == 2) return v[idx];
+    const R e = exp_(x);
+    if (MODE == 1) v[idx] = e;
+    return e;
+  }
+  CS2_HD R tp1(R x) {
+    if (MODE == 2) return v[CK_TP1];
+    const R e = one_plus_tanh<R>(x);
+    if (MODE == 1) v[CK_TP1] = e;
+    return e;
+  }
+};
+
 // ---------------------------------------------------------------------------------------
 // thermodynamic functions (common/_stencils/fcttre.py:22-57) -- only the non-LPHYLIN NL path
 // ---------------------------------------------------------------------------------------
@@ -128,12 +155,12 @@ CS2_HD R saturation_point(const DevParams<R>& p, bool lphylin, R ap, R t) {
 // ---------------------------------------------------------------------------------------
 // saturation adjustment step (nonlinear/_stencils/cuadjtqs.py:22-35)
 // ---------------------------------------------------------------------------------------
-template <class R>
-CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t, R& q, AdjStep<R>& s) {
+template <class R, class X>
+CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t, R& q, AdjStep<R>& s, X& x, int ck) {
   s.t = t;
   s.q = q;
   s.rt = rcp(t - z4);
-  s.foeew = p.R2ES * exp_(z3 * (t - p.RTT) * s.rt);
+  s.foeew = p.R2ES * x.exp(ck, z3 * (t - p.RTT) * s.rt);
   const R qs1 = s.foeew * rap;
   s.clipped = qs1 > p.ZQMAX;
   s.qsc = s.clipped ? p.ZQMAX : qs1;
@@ -188,9 +215,9 @@ CS2_HD void adj_step_ad(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, c
 //   ad_ref  : second freezing test on the pre-adjustment temperature (AD stencil literal,
 //             adjoint/_stencils/cloudsc2.py:427); false for NL / TL / consistent AD.
 // ---------------------------------------------------------------------------------------
-template <class R, class C>
+template <class R, class C, class X>
 CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R crh2, bool conv_ok, R aph_s,
-                      bool ad_ref, Carry<R>& c, LevelOut<R>& o, Traj<R>& tr) {
+                      bool ad_ref, Carry<R>& c, LevelOut<R>& o, Traj<R>& tr, X& x) {
   const R one = R(1), zero = R(0);
   // first guess (:104,115-117)
   tr.t0 = in.t + p.dt * in.tnd_t;
@@ -226,7 +253,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   R esdp;
   if (C::TETENS) {
     if (tr.cold) {
-      tr.tp1 = one_plus_tanh<R>(R(0.17) * (t0 - p.RLPTRC));
+      tr.tp1 = x.tp1(R(0.17) * (t0 - p.RLPTRC));
       tr.fwat = R(0.545) * tr.tp1;
       tr.z3es = p.R3IES;
       tr.z4es = p.R4IES;
@@ -238,7 +265,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
       tr.z4es = p.R4LES;
       tr.rtm4 = tr.rtw;
     }
-    tr.foeew = p.R2ES * exp_(tr.z3es * (t0 - p.RTT) * tr.rtm4);
+    tr.foeew = p.R2ES * x.exp(CK_FOEEW, tr.z3es * (t0 - p.RTT) * tr.rtm4);
     const R esdp1 = tr.foeew * tr.rap;
     tr.clip_esdp = esdp1 > p.ZQMAX;
     esdp = tr.clip_esdp ? p.ZQMAX : esdp1;
@@ -357,15 +384,15 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
     tr.rclc = rcp(tr.clc_o);
     tr.cldl = tr.qlwc1 * tr.rclc;
     const R xl = tr.cldl * p.rlcrit;
-    tr.ltmp1 = exp_(-(xl * xl));
-    tr.ltmp2 = exp_(-(p.ckcodtl * (one - tr.ltmp1)));
+    tr.ltmp1 = x.exp(CK_LTMP1, -(xl * xl));
+    tr.ltmp2 = x.exp(CK_LTMP2, -(p.ckcodtl * (one - tr.ltmp1)));
     tr.qlwc = tr.clc_o * tr.cldl * tr.ltmp2;
     tr.prr = tr.qlwc1 - tr.qlwc;
     tr.cldi = tr.qiwc1 * tr.rclc;
     const R xi = tr.cldi * p.ricrit;
-    tr.itmp11 = exp_(-(xi * xi));
-    tr.itmp12 = exp_(R(0.025) * (tr.tmelt - p.RTT));
-    tr.itmp2 = exp_(-(p.ckcodti * tr.itmp12 * (one - tr.itmp11)));
+    tr.itmp11 = x.exp(CK_ITMP11, -(xi * xi));
+    tr.itmp12 = x.exp(CK_ITMP12, R(0.025) * (tr.tmelt - p.RTT));
+    tr.itmp2 = x.exp(CK_ITMP2, -(p.ckcodti * tr.itmp12 * (one - tr.itmp11)));
     tr.qiwc = tr.clc_o * tr.cldi * tr.itmp2;
     tr.prs = tr.qiwc1 - tr.qiwc;
   } else {
@@ -432,8 +459,8 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   tr.z5c = tr.warmc ? p.R5ALVCP : p.R5ALSCP;
   tr.zalc = tr.warmc ? p.RALVDCP : p.RALSDCP;
   R t = tr.t3, q = tr.qa;
-  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sb);
-  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sa);
+  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sb, x, CK_SB);
+  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sa, x, CK_SA);
   tr.tpost = t;
   tr.qpost = q;
 

@@ -40,7 +40,7 @@ def make_grid_state(block: str, dtype, ncol: int, nz: int = 137):
 
 
 def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_predicates: str = "tl",
-                   lregcl: bool = True, **flags) -> Dict[str, Any]:
+                   lregcl: bool = True, ad_trajectory: str = "recompute", **flags) -> Dict[str, Any]:
     """saturation -> NL -> increment -> TL -> AD (symmetry pipeline) on the GPU."""
     cfg, grid, state = make_grid_state(block, dtype, ncol)
     p = iox.ifs_defaults()
@@ -61,7 +61,7 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
         return out
 
     st = SymmetryTest(grid, 0.01, 1, lphylin, ldrain1d, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"],
-                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates)
+                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates, ad_trajectory=ad_trajectory)
     # run the pipeline step by step to keep host copies of the TL outputs before AD consumes them
     st.diags_sat = st.saturation(state, out=st.diags_sat)
     state.update(st.diags_sat)

@@ -69,6 +69,20 @@ def test_ad_reference_predicates_match_literal_oracle():
     H.assert_fields_close(out["diags_ad"], ref["diags_ad"], 1e-12, "AD(reference) diagnostics: ")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_ad_checkpoint_mode_equals_recompute(dtype):
+    """CS2_AD_CHECKPOINT replays the recorded transcendentals instead of recomputing them: same result as
+    CS2_AD_RECOMPUTE up to FMA-contraction differences between the two kernel instantiations."""
+    a = gh().run_components(block="base", dtype=dtype, ncol=333, ad_trajectory="recompute")
+    b = gh().run_components(block="base", dtype=dtype, ncol=333, ad_trajectory="checkpoint")
+    tol = 1e-13 if dtype == np.float64 else 1e-5
+    for group in ("tends_ad", "diags_ad"):
+        H.assert_fields_close(b[group], a[group], tol, f"checkpoint vs recompute {group}: ")
+    for k, v in b["seeds_after"].items():
+        assert not v.any(), k
+    assert b["symmetry_norm3_max"] < 1e4 if dtype == np.float64 else True
+
+
 @pytest.mark.parametrize("flags", [dict(levapls2=True), dict(ldrain1d=True), dict(lphylin=False)])
 def test_nl_flag_paths(flags):
     out = gh().run_components(block="base", dtype=np.float64, ncol=100, nl_only=True, **flags)

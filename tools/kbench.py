@@ -21,7 +21,7 @@ from cloudsc2_b200.physics.adjoint.validation import SymmetryTest
 from cloudsc2_b200.physics.common.saturation import Saturation
 from cloudsc2_b200.physics.nonlinear.microphysics import Cloudsc2NL
 
-ELEMS = {"nl": 3567, "tl": 7134, "ad": 8508, "sat": 411}
+ELEMS = {"nl": 3567, "tl": 7134, "ad": 8508, "ad_ckpt": 8508, "sat": 411}
 
 
 def time_call(fn, reps):
@@ -68,18 +68,21 @@ def main():
         tn, dg = nl(state, dt)
         st = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg)
         st(state, dt, enable_validation=False)
+        st_ck = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg, ad_trajectory="checkpoint")
+        st_ck.tends_tl, st_ck.diags_tl, st_ck.tends_ad, st_ck.diags_ad = st.tends_tl, st.diags_tl, st.tends_ad, st.diags_ad
         res = {"columns": ncol, "precision": args.precision}
         for name, fn in (
             ("sat", lambda: sat(state, out={"f_qsat": state["f_qsat"]})),
             ("nl", lambda: nl(state, dt, out_tendencies=tn, out_diagnostics=dg)),
             ("tl", lambda: st.cloudsc2_tl(state, dt, out_tendencies=st.tends_tl, out_diagnostics=st.diags_tl)),
             ("ad", lambda: st.cloudsc2_ad(state, dt, out_tendencies=st.tends_ad, out_diagnostics=st.diags_ad)),
+            ("ad_ckpt", lambda: st_ck.cloudsc2_ad(state, dt, out_tendencies=st.tends_ad, out_diagnostics=st.diags_ad)),
         ):
             ms = time_call(fn, args.reps)
             gbs = ELEMS[name] * es * ncol / ms / 1e6
             res[name] = {"ms": round(ms, 4), "Mcol_s": round(ncol / ms / 1e3, 2), "GBs": round(gbs, 1), "frac": round(gbs / 6541.8, 4)}
         print(json.dumps(res), flush=True)
-        del st, nl, sat, state, tn, dg
+        del st, st_ck, nl, sat, state, tn, dg
         torch.cuda.empty_cache()
 
 
