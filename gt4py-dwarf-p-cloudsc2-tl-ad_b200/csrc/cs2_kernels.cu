@@ -68,10 +68,20 @@ template <class R>
 __global__ void __launch_bounds__(kPointBlock)
 saturation_kernel(const __grid_constant__ cs2::DevParams<R> p, int lphylin, const R* __restrict__ ap,
                   const R* __restrict__ t, R* __restrict__ qsat, int64_t ncol, int64_t S) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // two columns per thread (independent chains for the FP64 pipe), 16-byte accesses
+  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i >= ncol) return;
   const int64_t off = int64_t(blockIdx.y) * S + i;
-  qsat[off] = cs2::saturation_point<R>(p, lphylin != 0, ap[off], t[off]);
+  if (i + 1 < ncol) {
+    using V = typename cs2::Vec2<R>::type;
+    const V a = *reinterpret_cast<const V*>(ap + off), tt = *reinterpret_cast<const V*>(t + off);
+    V q;
+    q.x = cs2::saturation_point<R>(p, lphylin != 0, a.x, tt.x);
+    q.y = cs2::saturation_point<R>(p, lphylin != 0, a.y, tt.y);
+    *reinterpret_cast<V*>(qsat + off) = q;
+  } else {
+    qsat[off] = cs2::saturation_point<R>(p, lphylin != 0, ap[off], t[off]);
+  }
 }
 
 template <class R>
@@ -125,8 +135,14 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
                                                jsel_out, ck);
 }
 
+#ifndef CS2_TL_MINB
+#define CS2_TL_MINB 1
+#endif
+#ifndef CS2_AD_MINB
+#define CS2_AD_MINB 1
+#endif
 template <class R>
-__global__ void __launch_bounds__(kColumnBlock)
+__global__ void __launch_bounds__(kColumnBlock, CS2_TL_MINB)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
@@ -139,7 +155,7 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
 }
 
 template <class R, int NS>
-__global__ void __launch_bounds__(kColumnBlock)
+__global__ void __launch_bounds__(kColumnBlock, CS2_AD_MINB)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
@@ -295,7 +311,7 @@ template <class R>
 int launch_saturation(const cs2_dims* d, const cs2_params* P, const void* ap, const void* t, void* qsat, cudaStream_t st) {
   if (d->ncol == 0) return CS2_OK;
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, 1.0);
-  dim3 grid((unsigned)((d->ncol + kPointBlock - 1) / kPointBlock), (unsigned)d->nlev);
+  dim3 grid((unsigned)((d->ncol + 2 * kPointBlock - 1) / (2 * kPointBlock)), (unsigned)d->nlev);
   saturation_kernel<R><<<grid, kPointBlock, 0, st>>>(p, P->LPHYLIN, static_cast<const R*>(ap), static_cast<const R*>(t),
                                                     static_cast<R*>(qsat), d->ncol, d->ncol_stride);
   return check_cuda(cudaGetLastError(), "saturation launch");

@@ -135,21 +135,22 @@ CS2_HD R foeew_mixed(const DevParams<R>& p, R t, R alfa) {
   return p.R2ES * (alfa * el + (R(1) - alfa) * ei);
 }
 
-// saturation stencil, one point (common/_stencils/saturation.py:30-42)
+// saturation stencil, one point (common/_stencils/saturation.py:30-42).  The exponential of a phase whose
+// weight is exactly 0 is skipped (alfa is 0 below RTICE and 1 above RTWAT: 0 * finite + x == x bit for bit).
 template <class R>
 CS2_HD R saturation_point(const DevParams<R>& p, bool lphylin, R ap, R t) {
-  R qs;
-  if (lphylin) {
-    const R alfa = foealfa(p, t);
-    const R foeewl = p.R2ES * exp_(p.R3LES * (t - p.RTT) / (t - p.R4LES));
-    const R foeewi = p.R2ES * exp_(p.R3IES * (t - p.RTT) / (t - p.R4IES));
-    const R foeew = alfa * foeewl + (R(1) - alfa) * foeewi;
-    qs = min_(foeew / ap, p.QMAX);
-  } else {
-    const R ew = (p.kflag == 1) ? foeew_mixed(p, t, foealfcu(p, t)) : foeew_mixed(p, t, foealfa(p, t));
-    qs = min_(ew / ap, p.QMAX);
-  }
-  return qs / (R(1) - p.RETV * qs);
+  const R alfa = (lphylin || p.kflag != 1) ? foealfa(p, t) : foealfcu(p, t);
+  const R dtt = t - p.RTT;
+  R el = R(0), ei = R(0);
+  if (alfa > R(0)) el = exp_(p.R3LES * dtt * rcp(t - p.R4LES));
+  if (alfa < R(1)) ei = exp_(p.R3IES * dtt * rcp(t - p.R4IES));
+  R foeew;
+  if (lphylin)
+    foeew = alfa * (p.R2ES * el) + (R(1) - alfa) * (p.R2ES * ei);
+  else
+    foeew = p.R2ES * (alfa * el + (R(1) - alfa) * ei);
+  const R qs = min_(foeew * rcp(ap), p.QMAX);
+  return qs * rcp(R(1) - p.RETV * qs);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ def fp32_field_tolerances(ref32: Dict[str, np.ndarray], ref64: Dict[str, np.ndar
     inputs.  The TL/AD perturbation fields are differences of nearly equal quantities; there the fp32 oracle
     itself is only accurate to ~1e-5 of the field maximum, so two correct fp32 implementations (different
     libm, different but equivalent operation order) differ from each other by a small multiple of that.
-    The NL outputs are always held to the plain 1e-5."""
+    (Same for cloud cover near clc -> 0, where one fp32 ulp of qsat moves clc by > 1e-5.)"""
     tol = {}
     for name, r32 in ref32.items():
         r64 = ref64.get(name)
