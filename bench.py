@@ -311,35 +311,43 @@ def run_gpu_arm(args):
         del stest
         torch.cuda.empty_cache()
 
-    # ---- end to end through the same public calls with HOST buffers (pinned), every step:
-    #      H2D of the 15 NL state inputs + aph, saturation + NL, D2H of the 10 outputs
-    in_names = [n for n in state if isinstance(state[n], Field) and state[n].buffer.dim() == 2 and n != "f_qsat"
-                and not n.endswith("_i") and n in nl.input_grid_properties]
-    host_in = {n: state[n].buffer.detach().cpu().pin_memory() for n in in_names}
-    out_fields = {**{k: v for k, v in tends.items() if isinstance(v, Field)}, **{k: v for k, v in diags_nl.items() if isinstance(v, Field)}}
-    host_out = {n: torch.empty(f.buffer.shape, dtype=f.buffer.dtype).pin_memory() for n, f in out_fields.items()}
-    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    # ---- end to end with HOST buffers through the public host pipeline (cloudsc2_b200.pipeline): the batch lives in
+    #      pinned host memory as NPROMA-style column blocks; per block one H2D copy of the 15 packed inputs, the
+    #      Saturation + Cloudsc2NL component calls, one D2H copy of the 10 packed outputs; 3 streams, 3 device slots
+    from cloudsc2_b200.pipeline import IN_NAMES, NonlinearHostPipeline
 
-    def e2e_step():
-        for n, t in host_in.items():
-            state[n].buffer.copy_(t, non_blocking=True)
-        sat(state, out=diags)
-        nl(state, dt, out_tendencies=tends, out_diagnostics=diags_nl)
-        for n, f in out_fields.items():
-            host_out[n].copy_(f.buffer, non_blocking=True)
-
+    block_cols = min(args.e2e_block, ncol)
+    nblocks = -(-ncol // block_cols)
+    pipe = NonlinearHostPipeline(block_cols, NLEV, p, gt4py_config=cfg, timestep=dt, eta=state["f_eta"].numpy())
+    host_blocks = []
+    for b in range(nblocks):
+        blk = pipe.alloc_host_block()
+        lo, hi = b * block_cols, min((b + 1) * block_cols, ncol)
+        for n, name in enumerate(IN_NAMES):
+            blk["in"][n, :, : hi - lo].copy_(state[name].buffer[:, lo:hi])
+        host_blocks.append(blk)
+    h2d = pipe.h2d_bytes_per_block * nblocks
+    d2h = pipe.d2h_bytes_per_block * nblocks
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        e2e_step()
+        pipe.run(host_blocks)
     barrier()
+    pipe.launches = 0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
+        pipe.run(host_blocks)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     distributed.allreduce_max_(e2e_s)
     e2e_rate = ncol * world * e2e_steps / float(e2e_s.item())
+    # the pipelined result must equal the resident-state result (same kernels, same inputs)
+    from cloudsc2_b200.pipeline import OUT_NAMES
+
+    ref_t = tends["f_t"].buffer[:, : min(block_cols, ncol)]
+
+    got_t = host_blocks[0]["out"][OUT_NAMES.index("f_t")][:, : min(block_cols, ncol)].to(dev)
+    if not torch.equal(got_t, ref_t):
+        raise RuntimeError("host pipeline result differs from the resident-state result")
 
     if rank != 0:
         if world > 1:
@@ -369,7 +377,9 @@ def run_gpu_arm(args):
         },
         "variants": variants,
         "e2e": {"value": e2e_rate, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "pinned host buffers -> H2D -> Saturation + Cloudsc2NL components -> D2H of the 10 outputs"},
+                "steps": e2e_steps, "block_columns": block_cols, "gpu_launches": pipe.launches,
+                "what": "NonlinearHostPipeline: pinned host column blocks -> H2D (15 inputs) -> Saturation + Cloudsc2NL "
+                        "components -> D2H (10 outputs), 3 streams / 3 device slots, copies overlapped with kernels"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
@@ -402,6 +412,7 @@ def main():
     ap.add_argument("--columns", type=int, default=65536, help="columns per GPU")
     ap.add_argument("--precision", choices=("double", "single"), default="double")
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--e2e-block", type=int, default=4096, help="columns per host block of the e2e pipeline")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
