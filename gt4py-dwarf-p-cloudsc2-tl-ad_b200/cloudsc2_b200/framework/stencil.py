@@ -227,6 +227,26 @@ class Cloudsc2NLStencil(StencilObject):
                                        self._stream(ref)), "cs2_nl")
 
 
+@stencil_collection("cloudsc2_nl_perturbed")
+class Cloudsc2NLPerturbedStencil(StencilObject):
+    """Fusion of `perturbed_state` and `cloudsc2_nl` (no counterpart stencil in the reference; it computes what
+    tangent_linear/validation.py:167-176 computes with two stencil calls) -> cs2_nl_perturbed"""
+
+    def __call__(self, *, in_eta, dt, f, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None, **fields):
+        ref = fields["in_ap"]
+        dims = self._dims(ref, "in_ap")
+        self._check_domain(domain, dims.ncol, dims.nlev + 1)
+        base = _nl_struct(self, fields, dims)
+        incr = _lib.NLFields()
+        for name in _lib.NL_IN_NAMES:
+            setattr(incr, name, self._ptr(fields[name + "_i"], dims, name + "_i"))
+        tables = self._level_tables(in_eta, dims.nlev, dims, ref.device)
+        with self._Timer(self, exec_info, ref.device):
+            _lib.check(self.lib.cs2_nl_perturbed(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(),
+                                                 C.byref(base), C.byref(incr), float(f), self._stream(ref)),
+                       "cs2_nl_perturbed")
+
+
 @stencil_collection("cloudsc2_tl")
 class Cloudsc2TLStencil(StencilObject):
     """tangent_linear/_stencils/cloudsc2.py:23-774 -> cs2_tl"""
@@ -249,8 +269,9 @@ class Cloudsc2ADStencil(StencilObject):
 
     def __init__(self, externals: Dict[str, Any], gt4py_config: Any = None) -> None:
         super().__init__(externals, gt4py_config)
-        # trajectory handling of the backward sweep: "recompute" (default) or "checkpoint"
-        mode = str(externals.get("AD_TRAJECTORY", "recompute"))
+        # trajectory handling of the backward sweep: "checkpoint" (default, measured faster)
+        # or "recompute" (no workspace beyond 4 bytes per column)
+        mode = str(externals.get("AD_TRAJECTORY", "checkpoint"))
         if mode not in ("recompute", "checkpoint"):
             raise ValueError("AD_TRAJECTORY must be 'recompute' or 'checkpoint'")
         self.mode = _lib.CS2_AD_CHECKPOINT if mode == "checkpoint" else _lib.CS2_AD_RECOMPUTE

@@ -48,9 +48,10 @@ class Cloudsc2AD(ImplicitTendencyComponent):
         if ad_predicates not in ("tl", "reference"):
             raise ValueError("ad_predicates must be 'tl' or 'reference'")
         self.ad_predicates = ad_predicates
-        # "recompute": the backward sweep recomputes each level's trajectory; "checkpoint": the forward sweep
-        # stores the 9 transcendental results per point to an HBM workspace and the backward sweep replays them
-        self.ad_trajectory = ad_trajectory or os.environ.get("CS2_AD_TRAJECTORY", "recompute")
+        # "checkpoint" (default): the forward sweep stores the 9 transcendental results per point to an HBM workspace
+        # (72 B/point in fp64) and the backward sweep replays them; "recompute": the backward sweep recomputes each
+        # level's trajectory from the inputs (no workspace).  Measured on B200: checkpoint is 2-7 % faster.
+        self.ad_trajectory = ad_trajectory or os.environ.get("CS2_AD_TRAJECTORY", "checkpoint")
         externals = physics_externals(lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params, yrephli_params,
                                       yrncl_params, yrphnc_params, NLEV=nk,
                                       AD_TL_PREDICATES=(ad_predicates == "tl"), AD_TRAJECTORY=self.ad_trajectory)

@@ -57,3 +57,36 @@ class Cloudsc2NL(ImplicitTendencyComponent):
                 domain=self.computational_grid.grids[I, J, K - 1 / 2].shape,
                 validate_args=self.gt4py_config.validate_args, exec_info=self.gt4py_config.exec_info,
             )
+
+
+class PerturbedCloudsc2NL(Cloudsc2NL):
+    """`PerturbedState(factor)` followed by `Cloudsc2NL`, fused: the NL of the state x + factor * x_i, reading x
+    and x_i directly (32 input fields, no 16-field intermediate state).  Not in the reference; it is the opt-in
+    fast path of the Taylor test's inner loop (tangent_linear/validation.py:167-176) and returns bit-identical
+    results to the two separate components."""
+
+    def __init__(self, computational_grid, factor, lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params,
+                 yrephli_params, yrphnc_params, *, enable_checks=True, gt4py_config):
+        super().__init__(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params,
+                         yrephli_params, yrphnc_params, enable_checks=enable_checks, gt4py_config=gt4py_config)
+        self.f = gt4py_config.dtypes.float(factor)
+        self.cloudsc2_perturbed = self.compile_stencil("cloudsc2_nl_perturbed", self.cloudsc2.externals)
+
+    @cached_property
+    def input_grid_properties(self):
+        out = {"f_eta": props((K,), "")}
+        for n, (d, u) in NL_INPUTS.items():
+            out[f"f_{n}"] = props(d, u)
+            out[f"f_{n}_i"] = props(d, u)
+        return out
+
+    def array_call(self, state, timestep, out_tendencies, out_diagnostics, overwrite_tendencies):
+        kwargs = {f"in_{n}": state[f"f_{n}"] for n in NL_INPUTS}
+        kwargs.update({f"in_{n}_i": state[f"f_{n}_i"] for n in NL_INPUTS})
+        kwargs.update({f"out_{n}": out_diagnostics[f"f_{n}"] for n in NL_DIAGNOSTICS})
+        kwargs.update({f"out_tnd_{n}": out_tendencies[f"f_{n}"] for n in NL_TENDENCIES})
+        self.cloudsc2_perturbed(
+            **kwargs, in_eta=state["f_eta"], f=self.f, dt=self.gt4py_config.dtypes.float(timestep.total_seconds()),
+            origin=(0, 0, 0), domain=self.computational_grid.grids[I, J, K - 1 / 2].shape,
+            validate_args=self.gt4py_config.validate_args, exec_info=self.gt4py_config.exec_info,
+        )

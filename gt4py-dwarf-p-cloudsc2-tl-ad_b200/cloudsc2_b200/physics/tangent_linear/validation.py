@@ -17,7 +17,7 @@ from ...framework.timing import timing
 from ...reductions import TaylorSums
 from ..common.increment import PerturbedState, StateIncrement
 from ..common.saturation import Saturation
-from ..nonlinear.microphysics import Cloudsc2NL
+from ..nonlinear.microphysics import Cloudsc2NL, PerturbedCloudsc2NL
 from .microphysics import Cloudsc2TL
 
 TEND_NAMES = ("f_t", "f_q", "f_ql", "f_qi")
@@ -26,7 +26,11 @@ DIAG_NAMES = ("f_clc", "f_fhpsl", "f_fhpsn", "f_fplsl", "f_fplsn", "f_covptot")
 
 class TaylorTest:
     def __init__(self, computational_grid, factor1, factor2s, kflag, lphylin, ldrain1d, yoethf_params, yomcst_params,
-                 yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config):
+                 yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
+                 fused=False):
+        """`fused=True` replaces each PerturbedState -> Cloudsc2NL pair of the loop by one PerturbedCloudsc2NL call
+        (bit-identical norms, 42 instead of 74 field passes per factor); `state_p` is then not materialised."""
+        self.fused = fused
         self.f1 = factor1
         self.f2s = tuple(factor2s)
         yrncl_params.LREGCL = False  # no regularization in the Taylor test (:84-85)
@@ -38,6 +42,9 @@ class TaylorTest:
                                       yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, **kw)
         self.state_increment = StateIncrement(computational_grid, factor1, **kw)
         self.perturbed_states = [PerturbedState(computational_grid, f2, **kw) for f2 in self.f2s]
+        self.perturbed_nls = [PerturbedCloudsc2NL(computational_grid, f2, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                                  yrecldp_params, yrephli_params, yrphnc_params, **kw)
+                              for f2 in self.f2s] if fused else []
         self.diags_nl: Dict[str, Any] = {}
         self.diags_nl_p: Dict[str, Any] = {}
         self.diags_sat: Dict[str, Any] = {}
@@ -74,12 +81,17 @@ class TaylorTest:
         self._sums = torch.zeros((len(self.f2s), nfields, 2), dtype=torch.float64, device=dev)
         for i, perturbed_state in enumerate(self.perturbed_states):
             with timing("run"):
-                self.state_p = perturbed_state(state, out=self.state_p)
-                self.state_p["time"] = state["time"]
-                self.state_p["f_eta"] = state["f_eta"]
-                self.tends_nl_p, self.diags_nl_p = self.cloudsc2_nl(
-                    self.state_p, timestep, out_tendencies=self.tends_nl_p, out_diagnostics=self.diags_nl_p
-                )
+                if self.fused:
+                    self.tends_nl_p, self.diags_nl_p = self.perturbed_nls[i](
+                        state, timestep, out_tendencies=self.tends_nl_p, out_diagnostics=self.diags_nl_p
+                    )
+                else:
+                    self.state_p = perturbed_state(state, out=self.state_p)
+                    self.state_p["time"] = state["time"]
+                    self.state_p["f_eta"] = state["f_eta"]
+                    self.tends_nl_p, self.diags_nl_p = self.cloudsc2_nl(
+                        self.state_p, timestep, out_tendencies=self.tends_nl_p, out_diagnostics=self.diags_nl_p
+                    )
             with timing("norms"):
                 self.accumulate_sums(i)
 
@@ -92,8 +104,12 @@ class TaylorTest:
         """Device part of get_field_norm (:252-261): SUM(F_nl_p - F_nl) and SUM(F_tl_i) per field."""
         a: List[Any] = [self.tends_nl_p[n] for n in TEND_NAMES] + [self.diags_nl_p[n] for n in DIAG_NAMES]
         b: List[Any] = [self.tends_nl[n] for n in TEND_NAMES] + [self.diags_nl[n] for n in DIAG_NAMES]
-        c: List[Any] = [self.tends_tl[n + "_i"] for n in TEND_NAMES] + [self.diags_tl[n + "_i"] for n in DIAG_NAMES]
-        self._sums_op(a, b, c, self._sums[i].reshape(-1))
+        if i == 0:  # SUM(F_tl_i) does not depend on the factor: read the TL fields once
+            c: List[Any] = [self.tends_tl[n + "_i"] for n in TEND_NAMES] + [self.diags_tl[n + "_i"] for n in DIAG_NAMES]
+            self._sums_op(a, b, c, self._sums[0].reshape(-1))
+        else:
+            self._sums_op(a, b, None, self._sums[i].reshape(-1))
+            self._sums[i, :, 1] = self._sums[0, :, 1]
 
     def get_norm(self, i: int, sums: np.ndarray) -> float:
         """Host part of get_norm / get_field_norm (:219-261) from the reduced sums."""

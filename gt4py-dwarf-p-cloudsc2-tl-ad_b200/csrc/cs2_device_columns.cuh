@@ -1,11 +1,14 @@
-// Device-only column sweeps with a two-stage cp.async prefetch ring.
+// Device-only column sweeps with a cp.async prefetch buffer.
 //
 // Same level physics as cs2_columns.cuh (level_fwd / level_tl / level_ad); what differs is the
 // data movement.  A thread owns a column and, while it computes level k (several thousand cycles of
 // dependent FP64 work), the 16 / 32 / 27 inputs of the next level are already in flight: they are
 // copied global -> shared with cp.async (LDGSTS) into a slot private to the thread
-// (`stage[s][field][tid]`, conflict-free, no __syncthreads needed: a thread only ever reads what it
-// copied itself, after cp.async.wait_group 0).  This hides the HBM latency without spending a
+// (`v[field][tid]`, conflict-free, no __syncthreads needed: a thread only ever reads what it copied
+// itself, after cp.async.wait_group 0).  One stage is enough: at the top of a level the thread moves
+// its slots into registers and only then issues the copies of the next level into the same slots
+// (shared-memory reads and the much later asynchronous writes of one thread stay in program order).
+// This hides the HBM latency without spending a
 // single register on the prefetch, which matters because the register budget decides whether all
 // 65 536 columns of the headline case are resident in one wave.
 #pragma once
@@ -31,13 +34,13 @@ struct Streams {
 
 template <class R, int N, int BLOCK>
 struct Ring {
-  R v[2][N][BLOCK];
+  R v[N][BLOCK];
 };
 
 template <class R, int N, int BLOCK>
-__device__ __forceinline__ void ring_issue(Ring<R, N, BLOCK>& ring, const Streams<R, N>& in, int stage, uint32_t off) {
+__device__ __forceinline__ void ring_issue(Ring<R, N, BLOCK>& ring, const Streams<R, N>& in, uint32_t off) {
 #pragma unroll
-  for (int f = 0; f < N; ++f) cp_async<sizeof(R)>(&ring.v[stage][f][threadIdx.x], in.p[f] + off);
+  for (int f = 0; f < N; ++f) cp_async<sizeof(R)>(&ring.v[f][threadIdx.x], in.p[f] + off);
   cp_async_commit();
 }
 
@@ -55,25 +58,25 @@ inline Streams<R, I_NL> nl_streams(const NLFields<R>& f, int64_t S) {
 }
 
 template <class R, int N, int BLOCK>
-__device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, int stage, int base, R aph0, LevelIn<R>& in) {
+__device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, int base, R aph0, LevelIn<R>& in) {
   const int t = threadIdx.x;
-  in.ap = ring.v[stage][base + I_AP][t];
+  in.ap = ring.v[base + I_AP][t];
   in.aph0 = aph0;
-  in.aph1 = ring.v[stage][base + I_APH1][t];
-  in.lu1 = ring.v[stage][base + I_LU1][t];
-  in.lude = ring.v[stage][base + I_LUDE][t];
-  in.mfd = ring.v[stage][base + I_MFD][t];
-  in.mfu = ring.v[stage][base + I_MFU][t];
-  in.q = ring.v[stage][base + I_Q][t];
-  in.qi = ring.v[stage][base + I_QI][t];
-  in.ql = ring.v[stage][base + I_QL][t];
-  in.qsat = ring.v[stage][base + I_QSAT][t];
-  in.supsat = ring.v[stage][base + I_SUPSAT][t];
-  in.t = ring.v[stage][base + I_T][t];
-  in.tnd_q = ring.v[stage][base + I_TQ][t];
-  in.tnd_qi = ring.v[stage][base + I_TQI][t];
-  in.tnd_ql = ring.v[stage][base + I_TQL][t];
-  in.tnd_t = ring.v[stage][base + I_TT][t];
+  in.aph1 = ring.v[base + I_APH1][t];
+  in.lu1 = ring.v[base + I_LU1][t];
+  in.lude = ring.v[base + I_LUDE][t];
+  in.mfd = ring.v[base + I_MFD][t];
+  in.mfu = ring.v[base + I_MFU][t];
+  in.q = ring.v[base + I_Q][t];
+  in.qi = ring.v[base + I_QI][t];
+  in.ql = ring.v[base + I_QL][t];
+  in.qsat = ring.v[base + I_QSAT][t];
+  in.supsat = ring.v[base + I_SUPSAT][t];
+  in.t = ring.v[base + I_T][t];
+  in.tnd_q = ring.v[base + I_TQ][t];
+  in.tnd_qi = ring.v[base + I_TQI][t];
+  in.tnd_ql = ring.v[base + I_TQL][t];
+  in.tnd_t = ring.v[base + I_TT][t];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -84,7 +87,7 @@ template <class R, class C, int BLOCK, bool CKPT>
 __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const Streams<R, I_NL>& in_s, Ring<R, I_NL, BLOCK>& ring, uint32_t S,
                                               int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out, R* ck) {
-  ring_issue(ring, in_s, 0, i);  // level 0 is in flight while the tropopause scan runs
+  ring_issue(ring, in_s, i);  // level 0 is in flight while the tropopause scan runs
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   if (jsel_out && valid) jsel_out[i] = jsel;
   const int ncand = tab.nw + 1;
@@ -104,8 +107,8 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     const uint32_t off = uint32_t(k) * S + i;
     cp_async_wait_all();
     LevelIn<R> in;
-    ring_read_level(ring, k & 1, 0, aph0, in);
-    if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
+    ring_read_level(ring, 0, aph0, in);
+    if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, CKPT ? 1 : 0> x;
@@ -116,6 +119,86 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
 #pragma unroll
       for (int n = 0; n < CK_N; ++n) ck[uint32_t(n) * plane + off] = x.v[n];
     }
+    if (valid) {
+      f.clc[off] = o.clc;
+      f.covptot[off] = o.covptot;
+      f.o_tnd_q[off] = o.tnd_q;
+      f.o_tnd_qi[off] = o.tnd_qi;
+      f.o_tnd_ql[off] = o.tnd_ql;
+      f.o_tnd_t[off] = o.tnd_t;
+      const uint32_t offn = off + S;
+      f.fplsl[offn] = c.rfl;
+      f.fplsn[offn] = c.sfl;
+      f.fhpsl[offn] = -c.rfl * p.RLVTT;
+      f.fhpsn[offn] = -c.sfl * p.RLSTT;
+    }
+    aph0 = in.aph1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused perturbed NL: NL of the state x + fac * x_i without materialising it (what the Taylor test's
+// PerturbedState -> Cloudsc2NL pair computes; reference tangent_linear/validation.py:167-176).
+// Streams [0, 16) = x, [16, 32) = x_i.  The combination is the same single FMA the stand-alone
+// perturbed_state kernel performs, so the result is bit-identical to the unfused pair.
+// ---------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ R axpy(R fac, R xi, R x) {
+  return fac * xi + x;  // contracted to one FMA, like perturbed_state_kernel
+}
+
+template <class R>
+__device__ __forceinline__ int tropopause_candidate_pert(const DevParams<R>& p, const LevelTables<R>& tab, const R* t,
+                                                         const R* tnd_t, const R* t_i, const R* tnd_t_i, R fac, uint32_t S,
+                                                         uint32_t i) {
+  int jsel = 0;
+  int kprev = -2;
+  R tnext = R(0);
+  for (int j = 0; j < tab.nw; ++j) {
+    const int k = tab.wlev[j];
+    const uint32_t o = uint32_t(k) * S + i;
+    const R tk = (k == kprev + 1) ? tnext : (axpy(fac, t_i[o], t[o]) + p.dt * axpy(fac, tnd_t_i[o], tnd_t[o]));
+    tnext = axpy(fac, t_i[o + S], t[o + S]) + p.dt * axpy(fac, tnd_t_i[o + S], tnd_t[o + S]);
+    kprev = k;
+    if (tk > tnext) jsel = j + 1;
+  }
+  return jsel;
+}
+
+template <class R, class C, int BLOCK>
+__device__ __forceinline__ void dev_column_nl_pert(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                                   const NLFields<R>& g, R fac, const Streams<R, 2 * I_NL>& in_s,
+                                                   Ring<R, 2 * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
+                                                   bool valid) {
+  ring_issue(ring, in_s, i);
+  const int jsel = tropopause_candidate_pert(p, tab, f.t, f.tnd_t, g.t, g.tnd_t, fac, S, i);
+  const int ncand = tab.nw + 1;
+  Carry<R> c{R(0), R(0), R(0)};
+  const R aph_s = axpy(fac, g.aph[uint32_t(nlev) * S + i], f.aph[uint32_t(nlev) * S + i]);
+  R aph0 = axpy(fac, g.aph[i], f.aph[i]);
+  if (valid) {
+    f.fhpsl[i] = R(0);
+    f.fhpsn[i] = R(0);
+  }
+  for (int k = 0; k < nlev; ++k) {
+    const uint32_t off = uint32_t(k) * S + i;
+    cp_async_wait_all();
+    LevelIn<R> in, d;
+    ring_read_level(ring, 0, aph0, in);
+    ring_read_level(ring, I_NL, R(0), d);
+    if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
+    in.ap = axpy(fac, d.ap, in.ap);             in.aph1 = axpy(fac, d.aph1, in.aph1);
+    in.lu1 = axpy(fac, d.lu1, in.lu1);          in.lude = axpy(fac, d.lude, in.lude);
+    in.mfd = axpy(fac, d.mfd, in.mfd);          in.mfu = axpy(fac, d.mfu, in.mfu);
+    in.q = axpy(fac, d.q, in.q);                in.qi = axpy(fac, d.qi, in.qi);
+    in.ql = axpy(fac, d.ql, in.ql);             in.qsat = axpy(fac, d.qsat, in.qsat);
+    in.supsat = axpy(fac, d.supsat, in.supsat); in.t = axpy(fac, d.t, in.t);
+    in.tnd_q = axpy(fac, d.tnd_q, in.tnd_q);    in.tnd_qi = axpy(fac, d.tnd_qi, in.tnd_qi);
+    in.tnd_ql = axpy(fac, d.tnd_ql, in.tnd_ql); in.tnd_t = axpy(fac, d.tnd_t, in.tnd_t);
+    LevelOut<R> o;
+    Traj<R> tr;
+    Trans<R, 0> x;
+    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     if (valid) {
       f.clc[off] = o.clc;
       f.covptot[off] = o.covptot;
@@ -153,7 +236,7 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
                                               Ring<R, 2 * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
                                               bool valid) {
   using C = Cfg<false, true>;
-  ring_issue(ring, in_s, 0, i);
+  ring_issue(ring, in_s, i);
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   const int ncand = tab.nw + 1;
 
@@ -168,9 +251,9 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     const uint32_t off = uint32_t(k) * S + i;
     cp_async_wait_all();
     LevelIn<R> in, d;
-    ring_read_level(ring, k & 1, 0, aph0, in);
-    ring_read_level(ring, k & 1, I_NL, aph0_i, d);
-    if (k + 1 < nlev) ring_issue(ring, in_s, (k + 1) & 1, off + S);
+    ring_read_level(ring, 0, aph0, in);
+    ring_read_level(ring, I_NL, aph0_i, d);
+    if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
     LevelOut<R> o, oi;
     Traj<R> tr;
     Trans<R, 0> x;
@@ -229,7 +312,7 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
   constexpr bool CKPT = NS > B_N;
   using C = Cfg<false, true>;
   const bool ad_ref = !p.ad_tl_predicates;
-  ring_issue(ring, in_s, (nlev - 1) & 1, uint32_t(nlev - 1) * S + i);
+  ring_issue(ring, in_s, uint32_t(nlev - 1) * S + i);
   const int jsel = jsel_in[i];
   const int ncand = tab.nw + 1;
   const R aph_s = f.aph[uint32_t(nlev) * S + i];
@@ -240,33 +323,32 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
   R aph1 = aph_s;
   for (int k = nlev - 1; k >= 0; --k) {
     const uint32_t off = uint32_t(k) * S + i;
-    const int st = k & 1;
     cp_async_wait_all();
     LevelIn<R> in;
-    ring_read_level(ring, st, 0, R(0), in);
+    ring_read_level(ring, 0, R(0), in);
     in.aph0 = in.aph1;  // stream I_APH1 carries aph[k] in this sweep
     in.aph1 = aph1;
     Carry<R> c;
-    c.rfl = ring.v[st][B_FPLSL][t];
-    c.sfl = ring.v[st][B_FPLSN][t];
+    c.rfl = ring.v[B_FPLSL][t];
+    c.sfl = ring.v[B_FPLSN][t];
     c.covptot = R(0);  // only feeds the (disabled) evaporation branch
     LevelOut<R> so;
-    so.tnd_t = ring.v[st][B_S_TT][t];
-    so.tnd_q = ring.v[st][B_S_TQ][t];
-    so.tnd_ql = ring.v[st][B_S_TQL][t];
-    so.tnd_qi = ring.v[st][B_S_TQI][t];
-    so.clc = ring.v[st][B_S_CLC][t];
+    so.tnd_t = ring.v[B_S_TT][t];
+    so.tnd_q = ring.v[B_S_TQ][t];
+    so.tnd_ql = ring.v[B_S_TQL][t];
+    so.tnd_qi = ring.v[B_S_TQI][t];
+    so.clc = ring.v[B_S_CLC][t];
     so.covptot = R(0);
     // flux seeds at half level k+1 with the enthalpy-flux seeds folded in (AD :479-484,500-501)
-    R a_rfln = a_rfl + (ring.v[st][B_S_FPLSL][t] - ring.v[st][B_S_FHPSL][t] * p.RLVTT);
-    R a_sfln = a_sfl + (ring.v[st][B_S_FPLSN][t] - ring.v[st][B_S_FHPSN][t] * p.RLSTT);
+    R a_rfln = a_rfl + (ring.v[B_S_FPLSL][t] - ring.v[B_S_FHPSL][t] * p.RLVTT);
+    R a_sfln = a_sfl + (ring.v[B_S_FPLSN][t] - ring.v[B_S_FHPSN][t] * p.RLSTT);
 
     Trans<R, CKPT ? 2 : 0> x;
     if constexpr (CKPT) {
 #pragma unroll
-      for (int n = 0; n < CK_N; ++n) x.v[n] = ring.v[st][B_N + n][t];
+      for (int n = 0; n < CK_N; ++n) x.v[n] = ring.v[B_N + n][t];
     }
-    if (k > 0) ring_issue(ring, in_s, (k - 1) & 1, off - S);
+    if (k > 0) ring_issue(ring, in_s, off - S);
 
     LevelOut<R> o;
     Traj<R> tr;

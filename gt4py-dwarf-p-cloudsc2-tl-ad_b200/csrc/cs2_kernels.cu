@@ -135,14 +135,30 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
                                                jsel_out, ck);
 }
 
-#ifndef CS2_TL_MINB
-#define CS2_TL_MINB 1
+template <class R, class C>
+__global__ void __launch_bounds__(kColumnBlock, 7)
+nlp_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g, R fac,
+           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
+  __shared__ cs2::Ring<R, 2 * cs2::I_NL, kColumnBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_nl_pert<R, C, kColumnBlock>(p, tab, f, g, fac, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
+}
+
+// register caps of the two register-hungry kernels (measured on B200, profiles/README.md): spilling costs far
+// more than the occupancy it buys, the caps below are the largest spill-free values that changed the
+// compiler's allocation for the better
+#ifndef CS2_TL_MAXNREG
+#define CS2_TL_MAXNREG 255
 #endif
-#ifndef CS2_AD_MINB
-#define CS2_AD_MINB 1
+#ifndef CS2_AD_MAXNREG
+#define CS2_AD_MAXNREG 240
 #endif
 template <class R>
-__global__ void __launch_bounds__(kColumnBlock, CS2_TL_MINB)
+__global__ void __maxnreg__(CS2_TL_MAXNREG)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
@@ -155,7 +171,7 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
 }
 
 template <class R, int NS>
-__global__ void __launch_bounds__(kColumnBlock, CS2_AD_MINB)
+__global__ void __maxnreg__(CS2_AD_MAXNREG)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
@@ -359,6 +375,26 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   return check_cuda(cudaGetLastError(), "cloudsc2_nl launch");
 }
 
+template <class R>
+int launch_nl_pert(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
+                   const cs2_nl_fields* fi, double factor, cudaStream_t st) {
+  if (d->ncol == 0) return CS2_OK;
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f), ng = cs2::make_nl_fields<R>(*fi);
+  const cs2::Streams<R, 2 * cs2::I_NL> ns = cs2::tl_streams<R>(nf, ng, d->ncol_stride);
+  const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  const bool tetens = P->LPHYLIN || P->LDRAIN1D;
+#define CS2_LAUNCH_NLP(E, T) \
+  nlp_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ng, R(factor), ns, d->ncol, d->ncol_stride, d->nlev)
+  if (evap && tetens) CS2_LAUNCH_NLP(true, true);
+  else if (evap) CS2_LAUNCH_NLP(true, false);
+  else if (tetens) CS2_LAUNCH_NLP(false, true);
+  else CS2_LAUNCH_NLP(false, false);
+#undef CS2_LAUNCH_NLP
+  return check_cuda(cudaGetLastError(), "cloudsc2_nl_perturbed launch");
+}
+
 int check_tl_ad_flags(const cs2_params* P, const char* what) {
   if (P->LEVAPLS2 || P->LDRAIN1D)
     return fail(CS2_ERR_UNSUPPORTED,
@@ -503,6 +539,22 @@ int cs2_nl(const cs2_dims* dims, const cs2_params* params, double dt, const void
   return dims->dtype == CS2_F64
              ? launch_nl<double>(dims, params, dt, level_tables_dev, f, false, nullptr, nullptr, as_stream(stream))
              : launch_nl<float>(dims, params, dt, level_tables_dev, f, false, nullptr, nullptr, as_stream(stream));
+}
+
+int cs2_nl_perturbed(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+                     const cs2_nl_fields* f, const cs2_nl_fields* in_i, double factor, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_nl_perturbed: params or level tables NULL");
+  if (int rc = check_nl_fields(f, "cloudsc2_nl_perturbed fields")) return rc;
+  if (!in_i) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_nl_perturbed: increment fields NULL");
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(in_i), 16, "cloudsc2_nl_perturbed increments")) return rc;
+  cs2_nl_fields gi = *in_i;  // only the 16 in_* members of `in_i` are read; outputs alias the base outputs (unused)
+  gi.out_clc = f->out_clc; gi.out_covptot = f->out_covptot; gi.out_fhpsl = f->out_fhpsl; gi.out_fhpsn = f->out_fhpsn;
+  gi.out_fplsl = f->out_fplsl; gi.out_fplsn = f->out_fplsn; gi.out_tnd_q = f->out_tnd_q; gi.out_tnd_qi = f->out_tnd_qi;
+  gi.out_tnd_ql = f->out_tnd_ql; gi.out_tnd_t = f->out_tnd_t;
+  return dims->dtype == CS2_F64
+             ? launch_nl_pert<double>(dims, params, dt, level_tables_dev, f, &gi, factor, as_stream(stream))
+             : launch_nl_pert<float>(dims, params, dt, level_tables_dev, f, &gi, factor, as_stream(stream));
 }
 
 int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,

@@ -144,6 +144,17 @@ int cs2_nl(const cs2_dims* dims, const cs2_params* params, double dt,
            const void* level_tables_dev, const cs2_nl_fields* f, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused "perturbed_state" + "cloudsc2_nl": NL of the state x + factor * x_i without materialising it --
+ * the pair the Taylor test runs once per factor (tangent_linear/validation.py:167-176).  `f` carries
+ * the base state x (in_*) and the NL outputs (out_*); of `in_i` only the 16 in_* members (the x_i
+ * fields) are read.  Bit-identical to cs2_perturbed_state followed by cs2_nl (same single FMA per
+ * input), at 42 instead of 74 field passes through HBM.
+ * ------------------------------------------------------------------------------------- */
+int cs2_nl_perturbed(const cs2_dims* dims, const cs2_params* params, double dt,
+                     const void* level_tables_dev, const cs2_nl_fields* f, const cs2_nl_fields* in_i,
+                     double factor, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * "cloudsc2_tl" stencil -- tangent_linear/_stencils/cloudsc2.py:23-774, called from
  * Cloudsc2TL.array_call (tangent_linear/microphysics.py:162-242).  `traj` holds the NL
  * fields (trajectory inputs and outputs); `pert` holds the `_i` twin of each member.

@@ -40,7 +40,7 @@ def make_grid_state(block: str, dtype, ncol: int, nz: int = 137):
 
 
 def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_predicates: str = "tl",
-                   lregcl: bool = True, ad_trajectory: str = "recompute", **flags) -> Dict[str, Any]:
+                   lregcl: bool = True, ad_trajectory: str = "checkpoint", **flags) -> Dict[str, Any]:
     """saturation -> NL -> increment -> TL -> AD (symmetry pipeline) on the GPU."""
     cfg, grid, state = make_grid_state(block, dtype, ncol)
     p = iox.ifs_defaults()
@@ -88,11 +88,11 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
     return out
 
 
-def run_taylor(block: str = "base", dtype=np.float64, ncol: int = 100):
+def run_taylor(block: str = "base", dtype=np.float64, ncol: int = 100, fused: bool = False):
     cfg, grid, state = make_grid_state(block, dtype, ncol)
     p = iox.ifs_defaults()
     tt = TaylorTest(grid, 0.01, tuple(float(10 ** -(i + 1)) for i in range(10)), 1, True, False, p["yoethf"], p["yomcst"],
-                    p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg)
+                    p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg, fused=fused)
     norms = tt.run(state, timedelta(seconds=H.DT))
     return tt, norms
 

@@ -287,3 +287,15 @@ def test_host_pipeline_matches_oracle():
         out = pipe.unpack_outputs(blk, hi - lo)
         H.assert_fields_close({k: out[k] for k in tn}, {k: v[:, lo:hi] for k, v in tn.items()}, 1e-12, f"block {lo}: ")
         H.assert_fields_close({k: out[k] for k in dg}, {k: v[:, lo:hi] for k, v in dg.items()}, 1e-12, f"block {lo}: ")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_perturbed_nl_is_bit_identical(dtype):
+    """PerturbedCloudsc2NL == PerturbedState -> Cloudsc2NL, bit for bit, hence identical Taylor norms."""
+    tt_a, norms_a = gh().run_taylor("base", dtype, ncol=777, fused=False)
+    tt_b, norms_b = gh().run_taylor("base", dtype, ncol=777, fused=True)
+    assert np.array_equal(norms_a, norms_b), (norms_a, norms_b)
+    for d_a, d_b in ((tt_a.tends_nl_p, tt_b.tends_nl_p), (tt_a.diags_nl_p, tt_b.diags_nl_p)):
+        for k, v in d_a.items():
+            if hasattr(v, "numpy"):
+                assert np.array_equal(v.numpy(), d_b[k].numpy()), k

@@ -66,7 +66,7 @@ def main():
         state.update(sat(state))
         nl = Cloudsc2NL(grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrphnc"], gt4py_config=cfg)
         tn, dg = nl(state, dt)
-        st = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg)
+        st = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg, ad_trajectory="recompute")
         st(state, dt, enable_validation=False)
         st_ck = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"], p["yrphnc"], gt4py_config=cfg, ad_trajectory="checkpoint")
         st_ck.tends_tl, st_ck.diags_tl, st_ck.tends_ad, st_ck.diags_ad = st.tends_tl, st.diags_tl, st.tends_ad, st.diags_ad
