@@ -60,6 +60,10 @@ int check_nl_fields(const cs2_nl_fields* f, const char* what) {
 
 constexpr int kColumnBlock = 64;  // 65 536 columns = 1024 CTAs: one wave at 7 CTAs/SM (<= 144 registers)
 constexpr int kPointBlock = 256;
+#ifndef CS2_WIDE_BLOCK
+#define CS2_WIDE_BLOCK 64
+#endif
+constexpr int kWideBlock = CS2_WIDE_BLOCK;  // CTA size of the register-hungry TL / AD-backward kernels
 
 // ---------------------------------------------------------------------------------------
 // kernels
@@ -162,12 +166,12 @@ __global__ void __maxnreg__(CS2_TL_MAXNREG)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
-  __shared__ cs2::Ring<R, 2 * cs2::I_NL, kColumnBlock> ring;
+  __shared__ cs2::Ring<R, 2 * cs2::I_NL, kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_tl<R, kColumnBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
+  cs2::dev_column_tl<R, kWideBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 template <class R, int NS>
@@ -176,12 +180,12 @@ ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
               int64_t S, int nlev) {
-  __shared__ cs2::Ring<R, NS, kColumnBlock> ring;
+  __shared__ cs2::Ring<R, NS, kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_ad_bwd<R, kColumnBlock, NS>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
+  cs2::dev_column_ad_bwd<R, kWideBlock, NS>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 // ---- reductions -----------------------------------------------------------------------
@@ -433,14 +437,14 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   a.supsat = static_cast<R*>(adj->out_supsat_i); a.tnd_t = static_cast<R*>(adj->out_tnd_cml_t_i);
   a.tnd_q = static_cast<R*>(adj->out_tnd_cml_q_i); a.tnd_ql = static_cast<R*>(adj->out_tnd_cml_ql_i);
   a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
-  const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
+  const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*traj);
   if (ck)
-    ad_bwd_kernel<R, cs2::B_NCK><<<grid, kColumnBlock, 0, st>>>(
+    ad_bwd_kernel<R, cs2::B_NCK><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
         jsel, d->ncol, d->ncol_stride, d->nlev);
   else
-    ad_bwd_kernel<R, cs2::B_N><<<grid, kColumnBlock, 0, st>>>(
+    ad_bwd_kernel<R, cs2::B_N><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
         jsel, d->ncol, d->ncol_stride, d->nlev);
   if (int rc = check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch")) return rc;
@@ -565,15 +569,15 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
   if (int rc = check_nl_fields(pert, "cloudsc2_tl perturbation fields")) return rc;
   if (int rc = check_tl_ad_flags(params, "cloudsc2_tl")) return rc;
   if (dims->ncol == 0) return CS2_OK;
-  const unsigned grid = (unsigned)((dims->ncol + kColumnBlock - 1) / kColumnBlock);
+  const unsigned grid = (unsigned)((dims->ncol + kWideBlock - 1) / kWideBlock);
   if (dims->dtype == CS2_F64) {
     const auto f = cs2::make_nl_fields<double>(*traj), g = cs2::make_nl_fields<double>(*pert);
-    tl_kernel<double><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
+    tl_kernel<double><<<grid, kWideBlock, 0, as_stream(stream)>>>(
         cs2::make_dev_params<double>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<double>(f, g, dims->ncol_stride),
         dims->ncol, dims->ncol_stride, dims->nlev);
   } else {
     const auto f = cs2::make_nl_fields<float>(*traj), g = cs2::make_nl_fields<float>(*pert);
-    tl_kernel<float><<<grid, kColumnBlock, 0, as_stream(stream)>>>(
+    tl_kernel<float><<<grid, kWideBlock, 0, as_stream(stream)>>>(
         cs2::make_dev_params<float>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<float>(f, g, dims->ncol_stride),
         dims->ncol, dims->ncol_stride, dims->nlev);
   }

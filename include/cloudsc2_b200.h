@@ -171,9 +171,12 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt,
  *          (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).
  *   adj  : adjoint outputs.
  * `workspace_dev` must hold cs2_ad_workspace_bytes(dims, params, mode) bytes.
- * mode: CS2_AD_RECOMPUTE (backward sweep recomputes each level's trajectory from the inputs
- * and the level-entry carries) or CS2_AD_CHECKPOINT (forward sweep stores the transcendental
- * results of each level to the workspace; backward sweep reloads them).
+ * mode: CS2_AD_RECOMPUTE -- the backward sweep recomputes each level's trajectory from the inputs and
+ *       the level-entry fluxes (which are the trajectory outputs fplsl/fplsn); workspace = 4 B/column;
+ *       CS2_AD_CHECKPOINT -- the forward sweep also stores the 9 transcendental results of each point
+ *       (exp / 1+tanh values, 72 B/point in fp64) to the workspace and the backward sweep replays them
+ *       instead of re-evaluating them; the cheap algebra is recomputed in both modes.
+ *       Both give the same result up to FMA contraction; measured on B200: DESIGN.md section 3.
  * ------------------------------------------------------------------------------------- */
 enum { CS2_AD_RECOMPUTE = 0, CS2_AD_CHECKPOINT = 1 };
 
