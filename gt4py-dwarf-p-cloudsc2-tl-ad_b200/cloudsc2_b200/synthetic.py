@@ -60,6 +60,7 @@ def base_block(nz: int = KLEV, ncol: int = KLON, seed: int = 0, dtype=np.float64
     ts = rng.uniform(248.0, 306.0, size=ncol)
     ts[: ncol // 10] = rng.uniform(272.5, 277.5, size=ncol // 10)  # hug RTT / RTT+2
     eta_tp = rng.uniform(0.12, 0.36, size=ncol)
+    eta_tp[-max(ncol // 12, 1):] = 0.05  # no inversion inside 0.1 < eta < 0.4: the tropopause rule must fall back to 0.1
     kappa = rng.uniform(0.17, 0.21, size=ncol)
     t_trop = ts[None, :] * np.maximum(eta, 1e-6) ** kappa[None, :]
     t_tp = ts * eta_tp**kappa

@@ -109,3 +109,27 @@ def test_twin_ragged_column_counts(ncol):
     ttn, tdg = H.twin_nl(s, H.DT, P)
     H.assert_fields_close(ttn, tn, 1e-12)
     H.assert_fields_close(tdg, dg, 1e-12)
+
+
+@pytest.mark.parametrize("seed", [3, 11, 29])
+def test_twin_random_blocks_nl_tl_ad(seed):
+    """Other seeds of the synthetic generator (different branch patterns): NL, TL and AD of the kernel code vs oracle."""
+    P = H.externals(LREGCL=True)
+    st = H.make_state("base", np.float64, 100, seed=seed)
+    _, _, n3, o = H.oracle_symmetry(st, P, predicates="tl")
+    s = o["state"]
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P)
+    H.assert_fields_close(ttn, tn, 1e-12, f"seed {seed} NL: ")
+    H.assert_fields_close(tdg, dg, 1e-12, f"seed {seed} NL: ")
+    tt, td = H.twin_tl(s, H.DT, P)
+    H.assert_fields_close(tt, o["tends_tl"], 1e-12, f"seed {seed} TL: ")
+    H.assert_fields_close(td, o["diags_tl"], 1e-12, f"seed {seed} TL: ")
+    ad_in = dict(s)
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = o["tends_tl"][f"f_{x}_i"].copy()
+    ad_in.update({k: v.copy() for k, v in o["diags_tl"].items()})
+    tad, dad, _ = H.twin_ad(ad_in, H.DT, P, predicates="tl")
+    H.assert_fields_close(tad, o["tends_ad"], 1e-12, f"seed {seed} AD: ")
+    H.assert_fields_close(dad, o["diags_ad"], 1e-12, f"seed {seed} AD: ")
+    assert n3.max() < 1e4

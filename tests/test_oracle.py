@@ -79,3 +79,35 @@ def test_evaporation_branch_makes_covptot():
     s = H.with_diagnostics(H.make_state("base"), P)
     _, dg = H.onp.cloudsc2_nl(s, H.DT, P)
     assert dg["f_covptot"].any()
+
+
+def test_synthetic_block_exercises_both_sides_of_every_predicate():
+    """Branch census on the base block: the parity tests are only as strong as the
+    branches the inputs reach."""
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state("base"), P)
+    nz = 137
+    dt = H.DT
+    t = s["f_t"][:nz] + dt * s["f_tnd_cml_t"][:nz]
+    tn, dg = H.onp.cloudsc2_nl(s, dt, P)
+    clc = dg["f_clc"][:nz]
+    both = lambda m: bool(m.any() and (~m).any())  # noqa: E731
+    assert both(t < P["RTT"])                                   # p2 / p14 / p19 phase
+    assert both(t < P["RTICE"])                                 # p6 ice supersaturation
+    assert both(t > P["RTT"] + 2.0)                             # p12 melting possible
+    assert (clc == 0).any() and (clc == 1).any() and ((clc > 0) & (clc < 1)).any()   # p7 three-way
+    assert both(clc > P["ZEPS2"])                               # p13 autoconversion
+    gdp = P["RG"] / (s["f_aph"][1:] - s["f_aph"][:-1])
+    lude = dt * s["f_lude"][:nz] * gdp
+    lo1 = (lude >= P["RLMIN"]) & (s["f_lu"][1:] >= P["ZEPS2"])
+    assert both(lo1)                                            # p8 convective detrainment
+    assert (dg["f_fplsl"] > 0).any() and (dg["f_fplsn"] > 0).any()   # rain and snow both occur
+    # melting actually happens: rain flux appears below snow where t > RTT + 2
+    snow_in, warm = dg["f_fplsn"][:nz] > 0, t > P["RTT"] + 2.0
+    assert (snow_in & warm).any()
+    # the tropopause rule fires for some columns and not for others
+    trp = H.onp._trpaus(t, s["f_eta"], nz)
+    assert both(trp > 0.1)
+    # the saturation clip (esdp > ZQMAX) is reached at the model top
+    foeew = P["R2ES"] * np.exp(P["R3IES"] * (t - P["RTT"]) / (t - P["R4IES"]))
+    assert both(foeew / s["f_ap"][:nz] > P["ZQMAX"])
