@@ -85,7 +85,8 @@ class StencilObject:
         if nx != dims.ncol or stride != dims.ncol_stride or code != dims.dtype or nlevs != dims.nlev + 1:
             raise ValueError(f"{what}: layout {(nx, nlevs, stride, code)} differs from the call's "
                              f"{(dims.ncol, dims.nlev + 1, dims.ncol_stride, dims.dtype)}")
-        return arr.data_ptr()
+        # (torch reports data_ptr() == 0 for views without elements, e.g. an empty column shard)
+        return arr.untyped_storage().data_ptr() + arr.storage_offset() * arr.element_size()
 
     @staticmethod
     def _stream(ref: torch.Tensor) -> int:

@@ -20,6 +20,8 @@ class EtaLevels(DiagnosticComponent):
 
     def array_call(self, state, out):
         nz = self.computational_grid.grids[I, J, K].shape[2]
+        if self.computational_grid.nx < 1:
+            raise ValueError("EtaLevels needs column 0 of the (global) domain; this grid has no columns")
         # one device->host transfer of column 0 instead of the reference's nz scalar reads
         ap0 = state["f_ap"][0, 0, :nz].detach().cpu()
         aph_s = state["f_aph"][0, 0, nz].detach().cpu()

@@ -299,3 +299,52 @@ def test_fused_perturbed_nl_is_bit_identical(dtype):
         for k, v in d_a.items():
             if hasattr(v, "numpy"):
                 assert np.array_equal(v.numpy(), d_b[k].numpy()), k
+
+
+def test_empty_grid_is_a_no_op():
+    """nx = 0: nothing is launched, nothing fails."""
+    out = gh().run_components(block="base", dtype=np.float64, ncol=0, nl_only=True)
+    assert out["tends_nl"]["f_t"].shape == (138, 0)
+
+
+def test_one_million_columns_nl_tiling_property():
+    """BASELINE config 5 size on one GPU (1 048 576 columns x 137 levels, NL): every replicated 100-column block is
+    bit-identical to the first one, which equals the oracle.  The state is tiled on the device."""
+    from cloudsc2_b200 import iox, setup, synthetic
+    from cloudsc2_b200.framework.config import GridConfig
+    from cloudsc2_b200.framework.grid import ComputationalGrid
+    from cloudsc2_b200.physics.common.diagnostics import EtaLevels
+    from cloudsc2_b200.physics.common.saturation import Saturation
+    from cloudsc2_b200.physics.nonlinear.microphysics import Cloudsc2NL
+
+    g = gh()
+    ncol = 1 << 20
+    cfg = g.config_for(np.float64)
+    grid = ComputationalGrid(GridConfig(nx=ncol, ny=1, nz=137))
+    blk = synthetic.base_block()
+    small = ComputationalGrid(GridConfig(nx=100, ny=1, nz=137))
+    state = {}
+    for name, arr in blk.items():
+        fld = setup.zeros(grid, (setup.I, setup.J, setup.K - 1 / 2) if name == "f_aph" else (setup.I, setup.J, setup.K),
+                          gt4py_config=cfg, name=name)
+        dev_blk = torch.as_tensor(arr, device=fld.buffer.device)
+        reps = -(-ncol // 100)
+        fld.buffer[:, :ncol] = dev_blk.repeat(1, reps)[:, :ncol]
+        state[name] = fld
+    state.update(EtaLevels(grid, gt4py_config=cfg)(state))
+    p = iox.ifs_defaults()
+    state.update(Saturation(grid, 1, True, p["yoethf"], p["yomcst"], gt4py_config=cfg)(state))
+    nl = Cloudsc2NL(grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrphnc"], gt4py_config=cfg)
+    tn, dg = nl(state, timedelta(seconds=H.DT))
+    nfull = (ncol // 100) * 100
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state("base"), P)
+    rtn, rdg = H.onp.cloudsc2_nl(s, H.DT, P)
+    for name, fld in {**tn, **dg}.items():
+        if not hasattr(fld, "buffer"):
+            continue
+        buf = fld.buffer[:, :nfull].reshape(138, nfull // 100, 100)
+        assert bool((buf == buf[:, :1, :]).all().item()), name
+        first = buf[:, 0, :].cpu().numpy()
+        ref = {**rtn, **rdg}[name]
+        assert np.abs(ref).max() == 0 and np.abs(first).max() == 0 or H.field_err(first, ref) <= 1e-12, name
