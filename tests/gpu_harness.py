@@ -45,14 +45,15 @@ def make_grid_state(block: str, dtype, ncol: int, nz: int = 137):
 
 
 def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_predicates: str = "tl",
-                   lregcl: bool = True, ad_trajectory: str = "checkpoint", **flags) -> Dict[str, Any]:
+                   lregcl: bool = True, ad_trajectory: str = "checkpoint", nz: int = 137, dt_seconds: float = H.DT,
+                   **flags) -> Dict[str, Any]:
     """saturation -> NL -> increment -> TL -> AD (symmetry pipeline) on the GPU."""
-    cfg, grid, state = make_grid_state(block, dtype, ncol)
+    cfg, grid, state = make_grid_state(block, dtype, ncol, nz)
     p = iox.ifs_defaults()
     p["yrncl"].LREGCL = lregcl
     p["yrphnc"].LEVAPLS2 = bool(flags.get("levapls2", False))
     lphylin, ldrain1d = bool(flags.get("lphylin", True)), bool(flags.get("ldrain1d", False))
-    dt = timedelta(seconds=H.DT)
+    dt = timedelta(seconds=dt_seconds)
     out: Dict[str, Any] = {}
 
     sat = Saturation(grid, 1, lphylin, p["yoethf"], p["yomcst"], gt4py_config=cfg)

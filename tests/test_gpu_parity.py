@@ -348,3 +348,21 @@ def test_one_million_columns_nl_tiling_property():
         first = buf[:, 0, :].cpu().numpy()
         ref = {**rtn, **rdg}[name]
         assert np.abs(ref).max() == 0 and np.abs(first).max() == 0 or H.field_err(first, ref) <= 1e-12, name
+
+
+@pytest.mark.parametrize("nz,dt", [(60, 900.0), (20, 1800.0)])
+def test_other_level_counts_and_timesteps(nz, dt):
+    from cloudsc2_b200 import synthetic
+
+    out = gh().run_components(block="base", dtype=np.float64, ncol=100, nz=nz, dt_seconds=dt)
+    P = H.externals(LREGCL=True)
+    st = {k: np.ascontiguousarray(v) for k, v in synthetic.base_block(nz=nz).items()}
+    _, _, n3, ref = H.oracle_symmetry(st, P, dt=dt, predicates="tl")
+    tn, dg = H.onp.cloudsc2_nl(ref["state"], dt, P)
+    H.assert_fields_close(out["tends_nl"], tn, 1e-12)
+    H.assert_fields_close(out["diags_nl"], dg, 1e-12)
+    H.assert_fields_close(out["tends_tl"], ref["tends_tl"], 1e-12)
+    H.assert_fields_close(out["diags_tl"], ref["diags_tl"], 1e-12)
+    H.assert_fields_close(out["tends_ad"], ref["tends_ad"], 1e-12)
+    H.assert_fields_close(out["diags_ad"], ref["diags_ad"], 1e-12)
+    assert out["symmetry_norm3_max"] < 1e4

@@ -133,3 +133,31 @@ def test_twin_random_blocks_nl_tl_ad(seed):
     H.assert_fields_close(tad, o["tends_ad"], 1e-12, f"seed {seed} AD: ")
     H.assert_fields_close(dad, o["diags_ad"], 1e-12, f"seed {seed} AD: ")
     assert n3.max() < 1e4
+
+
+@pytest.mark.parametrize("nz,dt", [(60, 900.0), (137, 1200.0), (20, 3600.0)])
+def test_twin_other_level_counts_and_timesteps(nz, dt):
+    """Nothing in the kernels is specialised to 137 levels or dt = 3600 s."""
+    from cloudsc2_b200 import synthetic
+
+    P = H.externals(LREGCL=True)
+    st = {k: np.ascontiguousarray(v) for k, v in synthetic.base_block(nz=nz, ncol=64, seed=5).items()}
+    s = H.with_diagnostics(st, P)
+    tn, dg = H.onp.cloudsc2_nl(s, dt, P)
+    ttn, tdg = H.twin_nl(s, dt, P)
+    H.assert_fields_close(ttn, tn, 1e-12, f"nz={nz} NL: ")
+    H.assert_fields_close(tdg, dg, 1e-12, f"nz={nz} NL: ")
+    s.update(H.onp.state_increment(s, 0.01, ignore_supsat=True))
+    rt, rd = H.onp.cloudsc2_tl(s, dt, P)
+    tt, td = H.twin_tl(s, dt, P)
+    H.assert_fields_close(tt, rt, 1e-12, f"nz={nz} TL: ")
+    H.assert_fields_close(td, rd, 1e-12, f"nz={nz} TL: ")
+    ad_in = dict(s)
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = rt[f"f_{x}_i"].copy()
+    ad_in.update({k: v.copy() for k, v in rd.items()})
+    ref_in = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ad_in.items()}
+    rat, rad = H.onp.cloudsc2_ad(ref_in, dt, P, predicates="tl")
+    tad, dad, _ = H.twin_ad(ad_in, dt, P, predicates="tl")
+    H.assert_fields_close(tad, rat, 1e-12, f"nz={nz} AD: ")
+    H.assert_fields_close(dad, rad, 1e-12, f"nz={nz} AD: ")
