@@ -281,6 +281,23 @@ def run_gpu_arm(args):
     elapsed_ms, nl_ms = float(elapsed_ms.item()), float(nl_ms.item())
     launches = 2 * args.steps
 
+    # ---- FP64-pipe peak of this device (DFMA micro-benchmark, CUDA events)
+    fp64_peak = None
+    try:
+        lib = _lib.load()
+        blocks, iters = 148 * 16, 20000
+        scratch = torch.empty(blocks * 256, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.cs2_dfma_rate(scratch.data_ptr(), blocks, 200, stream), "cs2_dfma_rate")
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.cs2_dfma_rate(scratch.data_ptr(), blocks, iters, stream), "cs2_dfma_rate")
+        b.record()
+        torch.cuda.synchronize()
+        fp64_peak = blocks * 256 * 8 * iters * 2 / (a.elapsed_time(b) * 1e-3) / 1e12
+    except Exception:  # pragma: no cover
+        fp64_peak = None
+
     # ---- kernel-only variants (TL, AD) on the same columns, rank-local, outside the headline region
     variants = {}
     if not args.no_variants:
@@ -374,6 +391,12 @@ def run_gpu_arm(args):
             "frac": achieved / peak, "traffic": ncu_traffic("nl_kernel"),
             "algorithmic_bytes_per_column": ELEMS["nl"] * esize, "kernel_ms": nl_ms,
             "kernel_columns_per_s": ncol / (nl_ms * 1e-3), "peak_source": peak_src,
+            # second axis of the roofline: algorithmic flops (334 arithmetic ops + 15 transcendental calls per
+            # point, all branches) against the DFMA rate measured on this device just before
+            "fp64": {"peak_tflops_measured": fp64_peak, "algorithmic_flops_per_column": 349 * NLEV,
+                     "achieved_tflops": 349 * NLEV * ncol / (nl_ms * 1e-3) / 1e12,
+                     "frac": (349 * NLEV * ncol / (nl_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                     "note": "bytes are the slower axis: the HBM fraction is the roofline fraction"},
         },
         "variants": variants,
         "e2e": {"value": e2e_rate, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

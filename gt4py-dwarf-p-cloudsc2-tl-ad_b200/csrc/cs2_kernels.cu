@@ -188,6 +188,16 @@ ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
   cs2::dev_column_ad_bwd<R, kWideBlock, NS>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
+// ---- FP64 pipe micro-benchmark (the roofline's second axis: MEASURED_PEAKS.json has no FP64 entry) -----------
+__global__ void __launch_bounds__(256) dfma_rate_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // ---- reductions -----------------------------------------------------------------------
 constexpr int kMaxRedFields = 16;
 struct RedPtrs {
@@ -502,6 +512,13 @@ int cs2_level_tables_build(const cs2_params* params, int32_t nlev, int32_t dtype
   else
     build_tables<float>(*params, nlev, static_cast<const float*>(eta_host), tables_host);
   return CS2_OK;
+}
+
+int cs2_dfma_rate(double* scratch_dev, int32_t blocks, int32_t iters, void* stream) {
+  if (!scratch_dev) return fail(CS2_ERR_NULL_POINTER, "dfma_rate: scratch is NULL");
+  if (blocks < 1 || iters < 1) return fail(CS2_ERR_BAD_DIMS, "dfma_rate: blocks and iters must be positive");
+  dfma_rate_kernel<<<blocks, 256, 0, as_stream(stream)>>>(scratch_dev, iters, 0.999999, 1e-6);
+  return check_cuda(cudaGetLastError(), "dfma_rate launch");
 }
 
 int cs2_saturation(const cs2_dims* dims, const cs2_params* params, const void* in_ap, const void* in_t,

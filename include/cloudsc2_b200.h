@@ -92,6 +92,12 @@ const char* cs2_last_error(void);
 /* Number of CUDA devices visible to the library (0 without a GPU); < 0 on runtime error. */
 int cs2_device_count(void);
 
+/* Measurement helper: `blocks` CTAs of 256 threads each run 8 independent chains of `iters` dependent
+ * DFMAs (flops = blocks * 256 * 8 * iters * 2) and write one double per thread to `scratch_dev`
+ * (>= blocks * 256 doubles).  Timed with CUDA events by bench.py to put the FP64-pipe peak of the
+ * device next to the HBM peak (the roofline's second axis). */
+int cs2_dfma_rate(double* scratch_dev, int32_t blocks, int32_t iters, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Level tables.  Everything that depends on the level only -- `scalm = ZSCAL*max(eta-0.2,
  * ZEPS1)**0.2` (nonlinear/_stencils/cloudsc2.py:127) and the critical relative humidity
