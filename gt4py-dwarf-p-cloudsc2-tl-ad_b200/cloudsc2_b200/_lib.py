@@ -12,7 +12,7 @@ import os
 from typing import Any, Dict, Optional
 
 LIB_NAME = "libcloudsc2_b200.so"
-# CS2_LIB lets a developer A/B-test another build of the same CUDA library (tools/kbench.py); it never selects a
+# CS2_LIB lets a developer A/B-test another build of the same CUDA library (tests/kbench.py); it never selects a
 # different implementation: the file must export the same C ABI.
 LIB_PATH = os.environ.get("CS2_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 

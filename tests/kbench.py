@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Developer micro-benchmark: kernel-only times of NL / TL / AD (CUDA events) + a quick parity check.
-    python tools/kbench.py [--columns 65536] [--precision double] [--reps 20]
+"""Developer micro-benchmark (test infrastructure): kernel-only times of NL / TL / AD (CUDA events) + a quick parity
+check against the oracle.
+    python tests/kbench.py [--columns 65536] [--precision double] [--reps 20]
 """
 import argparse
 import json

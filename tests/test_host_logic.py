@@ -139,3 +139,19 @@ def test_world_size_2_gloo_reductions():
     )
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "DIST_OK rank=0" in res.stdout and "DIST_OK rank=1" in res.stdout
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU arms may touch oracle/ (or tests/helpers.py, which
+    imports it): the package and the drivers must not."""
+    import re
+
+    offenders = []
+    for top in ("gt4py-dwarf-p-cloudsc2-tl-ad_b200", "drivers"):
+        for dirpath, _, files in os.walk(os.path.join(H.ROOT, top)):
+            for fn in files:
+                if fn.endswith(".py"):
+                    text = open(os.path.join(dirpath, fn)).read()
+                    if re.search(r"^\s*(import|from)\s+(oracle|helpers|gpu_harness)\b", text, flags=re.M):
+                        offenders.append(os.path.join(dirpath, fn))
+    assert not offenders, offenders
