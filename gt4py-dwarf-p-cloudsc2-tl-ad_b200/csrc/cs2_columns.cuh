@@ -91,7 +91,8 @@ CS2_HD void load_level(const NLFields<R>& f, int64_t S, int64_t i, int k, R aph0
 // ---------------------------------------------------------------------------------------
 // NL column (also the forward sweep of AD: `jsel_out` keeps the tropopause candidate)
 // ---------------------------------------------------------------------------------------
-template <class R, class C>
+// LIN: keep the linearisation-friendly form of the trajectory (AD forward sweep); false for plain NL
+template <class R, class C, bool LIN = false>
 CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f, int64_t S, int nlev,
                       int64_t i, bool ad_ref, int32_t* jsel_out) {
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, S, i);
@@ -115,7 +116,7 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
+    level_fwd<R, C, LIN>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     f.clc[off] = o.clc;
     f.covptot[off] = o.covptot;
@@ -156,7 +157,7 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     LevelOut<R> o, oi;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
+    level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     const uint32_t offn = off + uint32_t(S);
@@ -207,7 +208,7 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
+    level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
 
     // seeds: tendencies / cloud cover at k, fluxes at half level k+1 with the enthalpy-flux
     // seeds folded in (AD :479-484,500-501); all consumed seeds are zeroed like the reference.

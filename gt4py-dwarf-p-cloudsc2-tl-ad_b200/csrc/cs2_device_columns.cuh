@@ -83,7 +83,7 @@ __device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, i
 // NL (and AD forward when jsel_out != nullptr)
 // ---------------------------------------------------------------------------------------
 // CKPT: also record the level's transcendental results into `ck` ([CK_N][nlev][S], CS2_AD_CHECKPOINT).
-template <class R, class C, int BLOCK, bool CKPT>
+template <class R, class C, int BLOCK, bool CKPT, bool LIN>
 __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const Streams<R, I_NL>& in_s, Ring<R, I_NL, BLOCK>& ring, uint32_t S,
                                               int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out, R* ck) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     Traj<R> tr;
     Trans<R, CKPT ? 1 : 0> x;
     if (CKPT) x.defaults();
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
+    level_fwd<R, C, LIN>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     if (CKPT && valid) {
       const uint32_t plane = uint32_t(nlev) * S;
 #pragma unroll
@@ -198,7 +198,7 @@ __device__ __forceinline__ void dev_column_nl_pert(const DevParams<R>& p, const 
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
+    level_fwd<R, C, false>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     if (valid) {
       f.clc[off] = o.clc;
       f.covptot[off] = o.covptot;
@@ -257,7 +257,7 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     LevelOut<R> o, oi;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
+    level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
     if (valid) {
       const uint32_t offn = off + S;
@@ -352,7 +352,7 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
 
     LevelOut<R> o;
     Traj<R> tr;
-    level_fwd<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
+    level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     LevelIn<R> ad;
     level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
     a_rfl = a_rfln;

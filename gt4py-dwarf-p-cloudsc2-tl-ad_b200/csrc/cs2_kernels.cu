@@ -125,7 +125,9 @@ perturbed_state_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int64_t nc
   for (int n = 0; n < CS2_NSTATE; ++n) f.out[n][off] = v[n] + fac * w[n];
 }
 
-template <class R, class C, bool CKPT>
+// CKPT: record the transcendentals (AD forward, checkpoint mode); LIN: AD forward sweep (trajectory evaluated in the
+// same form as the TL / AD-backward kernels evaluate it)
+template <class R, class C, bool CKPT, bool LIN>
 __global__ void __launch_bounds__(kColumnBlock, 7)
 nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
@@ -135,7 +137,7 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;  // out-of-range threads shadow the last column and store nothing
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_nl<R, C, kColumnBlock, CKPT>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0,
+  cs2::dev_column_nl<R, C, kColumnBlock, CKPT, LIN>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0,
                                                jsel_out, ck);
 }
 
@@ -376,11 +378,14 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
   const bool tetens = P->LPHYLIN || P->LDRAIN1D;
 #define CS2_LAUNCH_NL(E, T)                                                                                         \
-  nl_kernel<R, cs2::Cfg<E, T>, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev, \
-                                                                     ad_ref ? 1 : 0, jsel_out, nullptr)
+  nl_kernel<R, cs2::Cfg<E, T>, false, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
+                                                                            d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr)
   if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
-    nl_kernel<R, cs2::Cfg<false, true>, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
-                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
+    nl_kernel<R, cs2::Cfg<false, true>, true, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
+                                                                                   d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
+  else if (jsel_out)  // AD forward sweep, recompute mode
+    nl_kernel<R, cs2::Cfg<false, true>, false, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
+                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr);
   else if (evap && tetens) CS2_LAUNCH_NL(true, true);
   else if (evap) CS2_LAUNCH_NL(true, false);
   else if (tetens) CS2_LAUNCH_NL(false, true);

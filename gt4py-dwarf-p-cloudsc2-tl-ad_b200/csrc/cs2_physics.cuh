@@ -156,7 +156,9 @@ CS2_HD R saturation_point(const DevParams<R>& p, bool lphylin, R ap, R t) {
 // ---------------------------------------------------------------------------------------
 // saturation adjustment step (nonlinear/_stencils/cuadjtqs.py:22-35)
 // ---------------------------------------------------------------------------------------
-template <class R, class X>
+// LIN = the caller linearises about this trajectory (TL / AD): keep cor, qs and rden.  The NL kernels (LIN = false)
+// use an algebraically merged form with one reciprocal on the critical path instead of two in sequence.
+template <class R, bool LIN, class X>
 CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t, R& q, AdjStep<R>& s, X& x, int ck) {
   s.t = t;
   s.q = q;
@@ -165,11 +167,18 @@ CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t
   const R qs1 = s.foeew * rap;
   s.clipped = qs1 > p.ZQMAX;
   s.qsc = s.clipped ? p.ZQMAX : qs1;
-  s.cor = rcp(R(1) - p.RETV * s.qsc);
-  s.qs = s.qsc * s.cor;
   s.z2s = z5 * s.rt * s.rt;
-  s.rden = rcp(R(1) + s.qs * s.cor * s.z2s);
-  s.cond = (q - s.qs) * s.rden;
+  if (LIN) {
+    s.cor = rcp(R(1) - p.RETV * s.qsc);
+    s.qs = s.qsc * s.cor;
+    s.rden = rcp(R(1) + s.qs * s.cor * s.z2s);
+    s.cond = (q - s.qs) * s.rden;
+  } else {
+    // cond = (q - qsc/a) / (1 + qsc z2s / a^2) = a (q a - qsc) / (a^2 + qsc z2s),  a = 1 - RETV qsc
+    const R a = R(1) - p.RETV * s.qsc;
+    s.cond = a * (q * a - s.qsc) * rcp(a * a + s.qsc * s.z2s);
+    s.cor = s.qs = s.rden = R(0);
+  }
   t = t + zal * s.cond;
   q = q - s.cond;
 }
@@ -216,7 +225,7 @@ CS2_HD void adj_step_ad(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, c
 //   ad_ref  : second freezing test on the pre-adjustment temperature (AD stencil literal,
 //             adjoint/_stencils/cloudsc2.py:427); false for NL / TL / consistent AD.
 // ---------------------------------------------------------------------------------------
-template <class R, class C, class X>
+template <class R, class C, bool LIN, class X>
 CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R crh2, bool conv_ok, R aph_s,
                       bool ad_ref, Carry<R>& c, LevelOut<R>& o, Traj<R>& tr, X& x) {
   const R one = R(1), zero = R(0);
@@ -283,7 +292,13 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   tr.facw = p.R5LES * tr.rtw * tr.rtw;
   tr.faci = p.R5IES * tr.rti * tr.rti;
   tr.fac = tr.fwat * tr.facw + (one - tr.fwat) * tr.faci;
-  tr.cor = rcp(one - p.RETV * esdp);
+  // cor = 1 / (1 - RETV esdp); with esdp = foeew / ap unclipped this is ap / (ap - RETV foeew) = ap * fac2,
+  // and fac2 is needed by the subsidence term anyway: one reciprocal less per level
+  tr.fac2 = rcp(in.ap - p.RETV * tr.foeew);
+  if (LIN)
+    tr.cor = rcp(one - p.RETV * esdp);
+  else
+    tr.cor = tr.clip_esdp ? p.cor_clip : in.ap * tr.fac2;
   tr.dqsdtemp = tr.fac * tr.cor * in.qsat;
   tr.corqs = one + p.cons3 * tr.dqsdtemp;
   tr.qlim = min_(tr.q0, in.qsat);
@@ -335,7 +350,6 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   // compensating subsidence (:218-224)
   tr.fac1 = rcp(p.RD * t0);
   tr.rho = in.ap * tr.fac1;
-  tr.fac2 = rcp(in.ap - p.RETV * tr.foeew);
   tr.rodqsdp = -tr.rho * in.qsat * tr.fac2;
   tr.ldcp = tr.fwat * tr.lvdcp + (one - tr.fwat) * tr.lsdcp;
   tr.fac3 = rcp(one + tr.ldcp * tr.dqsdtemp);
@@ -460,8 +474,8 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   tr.z5c = tr.warmc ? p.R5ALVCP : p.R5ALSCP;
   tr.zalc = tr.warmc ? p.RALVDCP : p.RALSDCP;
   R t = tr.t3, q = tr.qa;
-  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sb, x, CK_SB);
-  adj_step(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sa, x, CK_SA);
+  adj_step<R, LIN>(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sb, x, CK_SB);
+  adj_step<R, LIN>(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, t, q, tr.sa, x, CK_SA);
   tr.tpost = t;
   tr.qpost = q;
 

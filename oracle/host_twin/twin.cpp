@@ -60,7 +60,7 @@ void run_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* table
   const bool ad_ref = !P->AD_TL_PREDICATES;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < d->ncol; ++i) {
-    cs2::column_nl<R, cs2::Cfg<false, true>>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, jsel);
+    cs2::column_nl<R, cs2::Cfg<false, true>, true>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, jsel);
     cs2::column_ad_bwd<R>(p, tab, nf, s, a, jsel, d->ncol_stride, d->nlev, i);
   }
 }
