@@ -161,3 +161,15 @@ def test_twin_other_level_counts_and_timesteps(nz, dt):
     tad, dad, _ = H.twin_ad(ad_in, dt, P, predicates="tl")
     H.assert_fields_close(tad, rat, 1e-12, f"nz={nz} AD: ")
     H.assert_fields_close(dad, rad, 1e-12, f"nz={nz} AD: ")
+
+
+@pytest.mark.parametrize("flags", [dict(LPHYLIN=True, KFLAG=1), dict(LPHYLIN=False, KFLAG=1), dict(LPHYLIN=False, KFLAG=0)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_twin_saturation_flag_paths(flags, dtype):
+    """All three branches of the saturation stencil (common/_stencils/saturation.py:30-41)."""
+    P = H.externals(**flags)
+    st = H.make_state("base", dtype)
+    ref = H.onp.saturation(st["f_ap"], st["f_t"], P)
+    got = H.twin_saturation(st["f_ap"], st["f_t"], P)
+    assert H.field_err(got, ref) <= H.TOL[np.dtype(dtype)]
+    assert not got[137].any()  # the padding level is outside the stencil's domain
