@@ -11,10 +11,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
-#include "cs2_device_columns.cuh"
+#include "cs2_bulk_columns.cuh"
 
 namespace {
 
@@ -139,6 +140,17 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
   cs2::dev_column_nl<R, C, kColumnBlock, CKPT, LIN>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0,
                                                jsel_out, ck);
+}
+
+template <class R, class C>
+__global__ void __launch_bounds__(kColumnBlock, 7)
+nl_bulk_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
+               int64_t ncol, int64_t S, int nlev) {
+  __shared__ cs2::BulkRing<R, cs2::I_NL, kColumnBlock> ring;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_nl_bulk<R, C, kColumnBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(blockIdx.x) * kColumnBlock,
+                                              uint32_t(ncol));
 }
 
 template <class R, class C>
@@ -380,7 +392,10 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
 #define CS2_LAUNCH_NL(E, T)                                                                                         \
   nl_kernel<R, cs2::Cfg<E, T>, false, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr)
-  if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
+  static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;  // experiment switch (profiles/README.md)
+  if (use_bulk && !jsel_out && !evap && tetens)
+    nl_bulk_kernel<R, cs2::Cfg<false, true>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
+  else if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
     nl_kernel<R, cs2::Cfg<false, true>, true, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
   else if (jsel_out)  // AD forward sweep, recompute mode
