@@ -94,7 +94,10 @@ __device__ __forceinline__ void dev_column_nl_bulk(const DevParams<R>& p, const 
     in.t = ring.v[st][I_T][slot];           in.tnd_q = ring.v[st][I_TQ][slot];     in.tnd_qi = ring.v[st][I_TQI][slot];
     in.tnd_ql = ring.v[st][I_TQL][slot];    in.tnd_t = ring.v[st][I_TT][slot];
     // every thread has now read stage st^1 (level k-1) and stage st (level k): stage st^1 may be refilled
-    __syncthreads();
+    if (BLOCK == 32)
+      __syncwarp();
+    else
+      __syncthreads();
     if (tid == 0 && k + 1 < nlev) bulk_issue(ring, in_s, st ^ 1, uint32_t(k + 1) * S + i0, seg_bytes);
     LevelOut<R> o;
     Traj<R> tr;

@@ -142,15 +142,19 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
                                                jsel_out, ck);
 }
 
+#ifndef CS2_BULK_BLOCK
+#define CS2_BULK_BLOCK 64
+#endif
+constexpr int kBulkBlock = CS2_BULK_BLOCK;
 template <class R, class C>
-__global__ void __launch_bounds__(kColumnBlock, 7)
+__global__ void __launch_bounds__(kBulkBlock, 448 / kBulkBlock)
 nl_bulk_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
                const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
                int64_t ncol, int64_t S, int nlev) {
-  __shared__ cs2::BulkRing<R, cs2::I_NL, kColumnBlock> ring;
+  __shared__ cs2::BulkRing<R, cs2::I_NL, kBulkBlock> ring;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_nl_bulk<R, C, kColumnBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(blockIdx.x) * kColumnBlock,
-                                              uint32_t(ncol));
+  cs2::dev_column_nl_bulk<R, C, kBulkBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(blockIdx.x) * kBulkBlock,
+                                            uint32_t(ncol));
 }
 
 template <class R, class C>
@@ -394,7 +398,8 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr)
   static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;  // experiment switch (profiles/README.md)
   if (use_bulk && !jsel_out && !evap && tetens)
-    nl_bulk_kernel<R, cs2::Cfg<false, true>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
+    nl_bulk_kernel<R, cs2::Cfg<false, true>><<<(unsigned)((d->ncol + kBulkBlock - 1) / kBulkBlock), kBulkBlock, 0, st>>>(
+        p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
   else if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
     nl_kernel<R, cs2::Cfg<false, true>, true, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
