@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(HERE, "..", "csrc"))
 OUT = os.path.join(HERE, "libcloudsc2_b200.so")
 SOURCES = ["cs2_kernels.cu"]
-HEADERS = ["cs2_common.cuh", "cs2_physics.cuh", "cs2_columns.cuh", os.path.join("..", "..", "include", "cloudsc2_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "cloudsc2_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

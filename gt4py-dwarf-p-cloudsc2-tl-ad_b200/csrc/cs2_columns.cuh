@@ -7,6 +7,7 @@
 #pragma once
 
 #include "cs2_physics.cuh"
+#include "cs2_physics_tl.cuh"
 
 namespace cs2 {
 
@@ -145,7 +146,9 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
   const int ncand = tab.nw + 1;
 
   Carry<R> c{R(0), R(0), R(0)}, ci{R(0), R(0), R(0)};
+#if defined(CS2_TL_SPLIT)
   const R aph_s = f.aph[int64_t(nlev) * S + i];
+#endif
   R aph0 = f.aph[i], aph0_i = g.aph[i];
   // half level 0 (TL :757-765)
   f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
@@ -155,10 +158,14 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     load_level(f, S, i, k, aph0, in);
     load_level(g, S, i, k, aph0_i, d);
     LevelOut<R> o, oi;
+#if defined(CS2_TL_SPLIT)  // the two-pass specification (level_fwd, then level_tl about its trajectory)
     Traj<R> tr;
     Trans<R, 0> x;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
+#else
+    level_fwd_tl<R>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, c, ci, o, oi);
+#endif
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     const uint32_t offn = off + uint32_t(S);
     f.clc[off] = o.clc;          g.clc[off] = oi.clc;

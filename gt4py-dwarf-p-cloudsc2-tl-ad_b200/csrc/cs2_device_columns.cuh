@@ -241,7 +241,9 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
   const int ncand = tab.nw + 1;
 
   Carry<R> c{R(0), R(0), R(0)}, ci{R(0), R(0), R(0)};
+#if defined(CS2_TL_SPLIT)
   const R aph_s = f.aph[uint32_t(nlev) * S + i];
+#endif
   R aph0 = f.aph[i], aph0_i = g.aph[i];
   if (valid) {  // half level 0 (TL :757-765)
     f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
@@ -255,10 +257,14 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     ring_read_level(ring, I_NL, aph0_i, d);
     if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
     LevelOut<R> o, oi;
+#if defined(CS2_TL_SPLIT)  // the two-pass specification (level_fwd, then level_tl about its trajectory)
     Traj<R> tr;
     Trans<R, 0> x;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
+#else
+    level_fwd_tl<R>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, c, ci, o, oi);
+#endif
     if (valid) {
       const uint32_t offn = off + S;
       f.clc[off] = o.clc;          g.clc[off] = oi.clc;

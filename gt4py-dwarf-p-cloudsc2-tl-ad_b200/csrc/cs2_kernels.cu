@@ -174,7 +174,7 @@ nlp_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__
 // more than the occupancy it buys, the caps below are the largest spill-free values that changed the
 // compiler's allocation for the better
 #ifndef CS2_TL_MAXNREG
-#define CS2_TL_MAXNREG 255
+#define CS2_TL_MAXNREG 128
 #endif
 #ifndef CS2_AD_MAXNREG
 #define CS2_AD_MAXNREG 240
