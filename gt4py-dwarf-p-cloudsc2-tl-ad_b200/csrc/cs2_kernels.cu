@@ -16,6 +16,7 @@
 #include <string>
 
 #include "cs2_bulk_columns.cuh"
+#include "cs2_split_columns.cuh"
 
 namespace {
 
@@ -155,6 +156,20 @@ nl_bulk_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restri
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
   cs2::dev_column_nl_bulk<R, C, kBulkBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(blockIdx.x) * kBulkBlock,
                                             uint32_t(ncol));
+}
+
+#ifndef CS2_SPLIT_CTAS
+#define CS2_SPLIT_CTAS 7
+#endif
+constexpr int kSplitCols = 64;  // columns per CTA of the split NL kernel (2 * kSplitCols threads)
+template <class R, class C, int NM>
+__global__ void __launch_bounds__(2 * kSplitCols, CS2_SPLIT_CTAS)
+nl_split_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+                const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
+                int64_t ncol, int64_t S, int nlev) {
+  __shared__ cs2::SplitShared<R, NM, kSplitCols> sh;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_nl_split<R, C, NM, kSplitCols>(p, tab, f, in_s, sh, uint32_t(S), nlev, uint32_t(ncol));
 }
 
 template <class R, class C>
@@ -397,7 +412,19 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   nl_kernel<R, cs2::Cfg<E, T>, false, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr)
   static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;  // experiment switch (profiles/README.md)
-  if (use_bulk && !jsel_out && !evap && tetens)
+  static const bool use_split = std::getenv("CS2_NL_SPLIT") != nullptr;
+  if (use_split && !jsel_out && !evap && d->nlev <= cs2::kSplitMaxLev) {
+    const unsigned sgrid = (unsigned)((d->ncol + kSplitCols - 1) / kSplitCols);
+#define CS2_LAUNCH_SPLIT(T, NM)                                                                                  \
+  nl_split_kernel<R, cs2::Cfg<false, T>, NM><<<sgrid, 2 * kSplitCols, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
+                                                                               d->nlev)
+    if (P->RVTMP2 == 0.0) {
+      if (tetens) CS2_LAUNCH_SPLIT(true, cs2::M_NZ); else CS2_LAUNCH_SPLIT(false, cs2::M_NZ);
+    } else {
+      if (tetens) CS2_LAUNCH_SPLIT(true, cs2::M_N); else CS2_LAUNCH_SPLIT(false, cs2::M_N);
+    }
+#undef CS2_LAUNCH_SPLIT
+  } else if (use_bulk && !jsel_out && !evap && tetens)
     nl_bulk_kernel<R, cs2::Cfg<false, true>><<<(unsigned)((d->ncol + kBulkBlock - 1) / kBulkBlock), kBulkBlock, 0, st>>>(
         p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
   else if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)

@@ -31,6 +31,19 @@ void run_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* table
 }
 
 template <class R>
+void run_nl_split(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f) {
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  const bool tetens = P->LPHYLIN || P->LDRAIN1D;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < d->ncol; ++i) {
+    if (tetens) cs2::column_nl_split<R, cs2::Cfg<false, true>>(p, tab, nf, d->ncol_stride, d->nlev, i);
+    else cs2::column_nl_split<R, cs2::Cfg<false, false>>(p, tab, nf, d->ncol_stride, d->nlev, i);
+  }
+}
+
+template <class R>
 void run_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
             const cs2_nl_fields* g) {
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
@@ -87,6 +100,12 @@ int twin_saturation(const cs2_dims* d, const cs2_params* P, const void* ap, cons
 }
 int twin_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f) {
   if (d->dtype == CS2_F64) run_nl<double>(d, P, dt, tables, f); else run_nl<float>(d, P, dt, tables, f);
+  return 0;
+}
+// the two half-level functions of the split NL kernel, evaluated back to back (evaporation branch off only)
+int twin_nl_split(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f) {
+  if (P->LEVAPLS2 || P->LDRAIN1D) return 1;
+  if (d->dtype == CS2_F64) run_nl_split<double>(d, P, dt, tables, f); else run_nl_split<float>(d, P, dt, tables, f);
   return 0;
 }
 int twin_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,

@@ -22,6 +22,20 @@ def test_twin_saturation_and_nl(block, dtype):
     H.assert_fields_close(tdg, dg, tol, "NL diagnostics: ")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("block", ["base", "cold"])
+@pytest.mark.parametrize("flags", [dict(), dict(LPHYLIN=False), dict(RVTMP2=0.61)])
+def test_twin_nl_split(block, dtype, flags):
+    """The two half-level functions of the split NL kernel (A: carry-independent, B: carry-dependent) give NL."""
+    P = H.externals(**flags)
+    s = H.with_diagnostics(H.make_state(block, dtype), P)
+    tol = H.TOL[np.dtype(dtype)]
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P, split=True)
+    H.assert_fields_close(ttn, tn, tol, f"NL split {flags} tendencies: ")
+    H.assert_fields_close(tdg, dg, tol, f"NL split {flags} diagnostics: ")
+
+
 @pytest.mark.parametrize("flags", [dict(LEVAPLS2=True), dict(LDRAIN1D=True), dict(LPHYLIN=False),
                                     dict(LPHYLIN=False, LEVAPLS2=True)])
 def test_twin_nl_flag_paths(flags):
