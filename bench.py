@@ -327,6 +327,26 @@ def run_gpu_arm(args):
             variants[name] = {"ms": ms, "columns_per_s": ncol / (ms * 1e-3), "achieved_GBs": gbs, "frac_hbm": gbs / peak}
         del stest
         torch.cuda.empty_cache()
+        if args.precision == "double":
+            # BASELINE.json config 2 names fp32 beside fp64: the same step (saturation + cloudsc2_nl) in single precision
+            cfg32 = GT4PyConfig(dtypes=DataTypes(bool=bool, float=np.float32, int=np.int64))
+            state32 = setup.get_synthetic_state(grid, gt4py_config=cfg32, column_offset=col0)
+            state32.update(EtaLevels(grid, gt4py_config=cfg32)(state32))
+            distributed.broadcast_eta(state32["f_eta"], src=0)
+            sat32 = Saturation(grid, 1, True, p["yoethf"], p["yomcst"], gt4py_config=cfg32)
+            nl32 = Cloudsc2NL(grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrphnc"],
+                              gt4py_config=cfg32)
+            d32 = sat32(state32)
+            state32.update(d32)
+            t32, g32 = nl32(state32, dt)
+            nl32_ms = time_call(lambda: nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32), reps=20)
+            step32_ms = time_call(lambda: (sat32(state32, out=d32), nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32)),
+                                  reps=20)
+            gbs = ELEMS["nl"] * 4 * ncol / (nl32_ms * 1e-3) / 1e9
+            variants["nl_fp32"] = {"ms": nl32_ms, "columns_per_s": ncol / (nl32_ms * 1e-3), "achieved_GBs": gbs,
+                                   "frac_hbm": gbs / peak, "step_ms": step32_ms, "step_columns_per_s": ncol / (step32_ms * 1e-3)}
+            del state32, t32, g32, d32
+            torch.cuda.empty_cache()
 
     # ---- end to end with HOST buffers through the public host pipeline (cloudsc2_b200.pipeline): the batch lives in
     #      pinned host memory as NPROMA-style column blocks; per block one H2D copy of the 15 packed inputs, the
