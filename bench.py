@@ -67,10 +67,23 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index: int):
-        self.index, self.proc, self.path = device_index, None, None
+    def __init__(self, device_index: int, enabled: bool = True):
+        self.index, self.proc, self.path, self.enabled = device_index, None, None, enabled
+
+    def count(self) -> int:
+        """Samples written so far (nvidia-smi needs 1-2 s to start on an 8-GPU box)."""
+        if self.proc is None or not self.path:
+            return 1 << 30  # nothing to wait for
+        try:
+            self.fh.flush()
+            with open(self.path) as fh:
+                return sum(1 for _ in fh)
+        except OSError:
+            return 1 << 30
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -255,12 +268,13 @@ def run_gpu_arm(args):
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(torch.cuda.current_device()) as clocks:
+    with ClockSampler(torch.cuda.current_device(), enabled=(rank == 0)) as clocks:
         # the sampler (20 ms period) spans warm-up + timed region: the timed region alone lasts only
         # steps x ~0.5 ms, so the warm-up is repeated until >= 0.25 s of load precede it
         t_load = time.perf_counter()
         nwarm = 0
-        while nwarm < args.warmup or time.perf_counter() - t_load < 0.25:
+        while (nwarm < args.warmup or time.perf_counter() - t_load < 0.25
+               or (clocks.count() < 3 and time.perf_counter() - t_load < 20.0)):  # the sampler must be running under load
             step()
             nwarm += 1
             if nwarm % 16 == 0:
