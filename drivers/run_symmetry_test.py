@@ -13,13 +13,13 @@ from cloudsc2_b200.framework.timing import Timer, timing
 from cloudsc2_b200.physics.adjoint.validation import SymmetryTest
 
 
-def core(config, io_config, ad_predicates=None):
+def core(config, io_config, ad_predicates=None, fused=False):
     grid, state, dt, p, _ = problem(config)
     cfg = config.gt4py_config
     st = SymmetryTest(grid, factor=0.01, kflag=1, lphylin=True, ldrain1d=False, yoethf_params=p["yoethf"],
                       yomcst_params=p["yomcst"], yrecldp_params=p["yrecldp"], yrephli_params=p["yrephli"],
                       yrncl_params=p["yrncl"], yrphnc_params=p["yrphnc"], enable_checks=config.sympl_enable_checks,
-                      gt4py_config=cfg, ad_predicates=ad_predicates)
+                      gt4py_config=cfg, ad_predicates=ad_predicates, fused=fused)
     passed = st(state, dt, enable_validation=True)
     cfg.reset_exec_info()
     runtime_l = []
@@ -45,13 +45,14 @@ def core(config, io_config, ad_predicates=None):
 @click.option("--output-csv-file", type=str, default=None)
 @click.option("--input-file", type=str, default=None)
 @click.option("--ad-predicates", type=click.Choice(("tl", "reference")), default=None)
-def main(enable_checks, num_cols, num_runs, precision, host_alias, output_csv_file, input_file, ad_predicates):
+@click.option("--fused/--unfused", is_flag=True, default=False, help="form the TL perturbation inside the TL kernel (same results)")
+def main(enable_checks, num_cols, num_runs, precision, host_alias, output_csv_file, input_file, ad_predicates, fused):
     config = (DEFAULT_CONFIG.with_precision(precision).with_checks(enable_checks).with_num_cols(num_cols or 100)
               .with_num_runs(num_runs))
     if input_file:
         config.input_file = input_file
     io_config = DEFAULT_IO_CONFIG.with_output_csv_file(output_csv_file).with_host_name(host_alias)
-    raise SystemExit(0 if core(config, io_config, ad_predicates) else 1)
+    raise SystemExit(0 if core(config, io_config, ad_predicates, fused) else 1)
 
 
 if __name__ == "__main__":

@@ -45,7 +45,7 @@ def core(config, io_config, fused=False):
 @click.option("--host-alias", type=str, default=None)
 @click.option("--output-csv-file", type=str, default=None)
 @click.option("--input-file", type=str, default=None)
-@click.option("--fused/--unfused", is_flag=True, default=False, help="fuse PerturbedState into the NL kernel (same results)")
+@click.option("--fused/--unfused", is_flag=True, default=False, help="fuse PerturbedState into the NL kernel and StateIncrement into the TL kernel (same results)")
 def main(enable_checks, num_cols, num_runs, precision, host_alias, output_csv_file, input_file, fused):
     config = (DEFAULT_CONFIG.with_precision(precision).with_checks(enable_checks).with_num_cols(num_cols or 100)
               .with_num_runs(num_runs))

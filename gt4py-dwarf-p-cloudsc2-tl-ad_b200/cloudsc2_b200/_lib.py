@@ -92,6 +92,11 @@ SIGNATURES = {
     "cs2_state_increment": (C.c_int, [C.POINTER(Dims), C.c_double, C.c_int32, PtrArray16, PtrArray16, C.c_void_p]),
     "cs2_perturbed_state": (C.c_int, [C.POINTER(Dims), C.c_double, PtrArray16, PtrArray16, PtrArray16, C.c_void_p]),
     "cs2_nl": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.c_void_p]),
+    "cs2_tl_increment": (
+        C.c_int,
+        [C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.POINTER(NLFields), C.c_double,
+         C.c_int32, C.c_void_p],
+    ),
     "cs2_nl_perturbed": (
         C.c_int,
         [C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.POINTER(NLFields), C.c_double,

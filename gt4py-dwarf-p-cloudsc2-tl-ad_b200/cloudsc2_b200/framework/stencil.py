@@ -264,6 +264,30 @@ class Cloudsc2TLStencil(StencilObject):
                                        C.byref(g), self._stream(ref)), "cs2_tl")
 
 
+@stencil_collection("cloudsc2_tl_increment")
+class Cloudsc2TLIncrementStencil(StencilObject):
+    """Fusion of `state_increment` and `cloudsc2_tl` (tangent_linear/validation.py:158-162 and
+    adjoint/validation.py:136-140 run them back to back) -> cs2_tl_increment.  Takes the trajectory inputs `in_*`,
+    the factor `f` and both output sets; the `in_*_i` perturbations are formed in the kernel as f * in_*."""
+
+    def __call__(self, *, in_eta, dt, f, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None, **fields):
+        ref = fields["in_ap"]
+        dims = self._dims(ref, "in_ap")
+        self._check_domain(domain, dims.ncol, dims.nlev + 1)
+        traj = _nl_struct(self, fields, dims)
+        pert = _lib.NLFields()
+        for name in _lib.NL_OUT_NAMES:
+            setattr(pert, name, self._ptr(fields[name + "_i"], dims, name + "_i"))
+        tables = self._level_tables(in_eta, dims.nlev, dims, ref.device)
+        with self._Timer(self, exec_info, ref.device):
+            _lib.check(
+                self.lib.cs2_tl_increment(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(), C.byref(traj),
+                                          C.byref(pert), float(f), int(bool(self.externals.get("IGNORE_SUPSAT", False))),
+                                          self._stream(ref)),
+                "cs2_tl_increment",
+            )
+
+
 @stencil_collection("cloudsc2_ad")
 class Cloudsc2ADStencil(StencilObject):
     """adjoint/_stencils/cloudsc2.py:24-996 -> cs2_ad"""

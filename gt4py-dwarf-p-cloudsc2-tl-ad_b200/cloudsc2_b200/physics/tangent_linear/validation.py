@@ -18,7 +18,7 @@ from ...reductions import TaylorSums
 from ..common.increment import PerturbedState, StateIncrement
 from ..common.saturation import Saturation
 from ..nonlinear.microphysics import Cloudsc2NL, PerturbedCloudsc2NL
-from .microphysics import Cloudsc2TL
+from .microphysics import Cloudsc2TL, IncrementedCloudsc2TL
 
 TEND_NAMES = ("f_t", "f_q", "f_ql", "f_qi")
 DIAG_NAMES = ("f_clc", "f_fhpsl", "f_fhpsn", "f_fplsl", "f_fplsn", "f_covptot")
@@ -29,7 +29,8 @@ class TaylorTest:
                  yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
                  fused=False):
         """`fused=True` replaces each PerturbedState -> Cloudsc2NL pair of the loop by one PerturbedCloudsc2NL call
-        (bit-identical norms, 42 instead of 74 field passes per factor); `state_p` is then not materialised."""
+        (bit-identical fields, 42 instead of 74 field passes per factor; `state_p` is then not materialised) and
+        lets the TL sweep form its perturbation factor1 * state itself (IncrementedCloudsc2TL: 16 fewer field reads)."""
         self.fused = fused
         self.f1 = factor1
         self.f2s = tuple(factor2s)
@@ -40,6 +41,9 @@ class TaylorTest:
                                       yrecldp_params, yrephli_params, yrphnc_params, **kw)
         self.cloudsc2_tl = Cloudsc2TL(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params,
                                       yrecldp_params, yrephli_params, yrncl_params, yrphnc_params, **kw)
+        self.cloudsc2_tl_inc = IncrementedCloudsc2TL(computational_grid, factor1, False, lphylin, ldrain1d, yoethf_params,
+                                                     yomcst_params, yrecldp_params, yrephli_params, yrncl_params,
+                                                     yrphnc_params, **kw) if fused else None
         self.state_increment = StateIncrement(computational_grid, factor1, **kw)
         self.perturbed_states = [PerturbedState(computational_grid, f2, **kw) for f2 in self.f2s]
         self.perturbed_nls = [PerturbedCloudsc2NL(computational_grid, f2, lphylin, ldrain1d, yoethf_params, yomcst_params,
@@ -72,7 +76,8 @@ class TaylorTest:
             )
             self.state_i = self.state_increment(state, out=self.state_i)
             state.update(self.state_i)
-            self.tends_tl, self.diags_tl = self.cloudsc2_tl(
+            tl = self.cloudsc2_tl_inc if self.fused else self.cloudsc2_tl  # fused: f_*_i formed in the sweep, not read
+            self.tends_tl, self.diags_tl = tl(
                 state, timestep, out_tendencies=self.tends_tl, out_diagnostics=self.diags_tl
             )
 

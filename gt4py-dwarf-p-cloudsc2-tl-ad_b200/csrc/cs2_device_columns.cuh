@@ -17,6 +17,9 @@
 
 namespace cs2 {
 
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -230,11 +233,14 @@ inline Streams<R, 2 * I_NL> tl_streams(const NLFields<R>& f, const NLFields<R>& 
   return s;
 }
 
-template <class R, int BLOCK>
+// INC: fused "state_increment" + "cloudsc2_tl" (cs2_tl_increment): the perturbation of every input is fac * input
+// (common/_stencils/state_increment.py:60-80; supsat_i = 0 with IGNORE_SUPSAT), formed in registers -- only the 16
+// trajectory inputs are streamed.
+template <class R, int BLOCK, bool INC = false>
 __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
-                                              const NLFields<R>& g, const Streams<R, 2 * I_NL>& in_s,
-                                              Ring<R, 2 * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
-                                              bool valid) {
+                                              const NLFields<R>& g, const Streams<R, (INC ? 1 : 2) * I_NL>& in_s,
+                                              Ring<R, (INC ? 1 : 2) * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
+                                              bool valid, R fac = R(0), bool ignore_supsat = false) {
   using C = Cfg<false, true>;
   ring_issue(ring, in_s, i);
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
@@ -244,7 +250,7 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
 #if defined(CS2_TL_SPLIT)
   const R aph_s = f.aph[uint32_t(nlev) * S + i];
 #endif
-  R aph0 = f.aph[i], aph0_i = g.aph[i];
+  R aph0 = f.aph[i], aph0_i = INC ? mul_rn(fac, aph0) : g.aph[i];
   if (valid) {  // half level 0 (TL :757-765)
     f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
     g.fplsl[i] = R(0); g.fplsn[i] = R(0); g.fhpsl[i] = R(0); g.fhpsn[i] = R(0);
@@ -254,7 +260,18 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     cp_async_wait_all();
     LevelIn<R> in, d;
     ring_read_level(ring, 0, aph0, in);
-    ring_read_level(ring, I_NL, aph0_i, d);
+    if constexpr (INC) {
+      // products rounded on their own (never contracted into a following FMA): bit-identical to state_increment's output
+      d.ap = mul_rn(fac, in.ap);         d.aph0 = aph0_i;                     d.aph1 = mul_rn(fac, in.aph1);
+      d.lu1 = mul_rn(fac, in.lu1);       d.lude = mul_rn(fac, in.lude);       d.mfd = mul_rn(fac, in.mfd);
+      d.mfu = mul_rn(fac, in.mfu);       d.q = mul_rn(fac, in.q);             d.qi = mul_rn(fac, in.qi);
+      d.ql = mul_rn(fac, in.ql);         d.qsat = mul_rn(fac, in.qsat);
+      d.supsat = ignore_supsat ? R(0) : mul_rn(fac, in.supsat);
+      d.t = mul_rn(fac, in.t);           d.tnd_q = mul_rn(fac, in.tnd_q);     d.tnd_qi = mul_rn(fac, in.tnd_qi);
+      d.tnd_ql = mul_rn(fac, in.tnd_ql); d.tnd_t = mul_rn(fac, in.tnd_t);
+    } else {
+      ring_read_level(ring, I_NL, aph0_i, d);
+    }
     if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
     LevelOut<R> o, oi;
 #if defined(CS2_TL_SPLIT)  // the two-pass specification (level_fwd, then level_tl about its trajectory)

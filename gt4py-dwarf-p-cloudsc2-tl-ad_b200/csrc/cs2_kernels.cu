@@ -207,6 +207,22 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
   cs2::dev_column_tl<R, kWideBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
+// fused state_increment + TL (cs2_tl_increment)
+template <class R>
+__global__ void __maxnreg__(CS2_TL_MAXNREG)
+tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+              const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
+              const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev, R fac,
+              int ignore_supsat) {
+  __shared__ cs2::Ring<R, cs2::I_NL, kWideBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_tl<R, kWideBlock, true>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, fac,
+                                          ignore_supsat != 0);
+}
+
 template <class R, int NS>
 __global__ void __maxnreg__(CS2_AD_MAXNREG)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
@@ -651,6 +667,32 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
         dims->ncol, dims->ncol_stride, dims->nlev);
   }
   return check_cuda(cudaGetLastError(), "cloudsc2_tl launch");
+}
+
+int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+                     const cs2_nl_fields* traj, const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat,
+                     void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl_increment: params or level tables NULL");
+  if (int rc = check_nl_fields(traj, "cloudsc2_tl_increment trajectory fields")) return rc;
+  if (!pert_out) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl_increment: perturbation outputs NULL");
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(pert_out) + 16, 10, "cloudsc2_tl_increment perturbation outputs"))
+    return rc;
+  if (int rc = check_tl_ad_flags(params, "cloudsc2_tl_increment")) return rc;
+  if (dims->ncol == 0) return CS2_OK;
+  const unsigned grid = (unsigned)((dims->ncol + kWideBlock - 1) / kWideBlock);
+  if (dims->dtype == CS2_F64) {
+    const auto f = cs2::make_nl_fields<double>(*traj), g = cs2::make_nl_fields<double>(*pert_out);
+    tl_inc_kernel<double><<<grid, kWideBlock, 0, as_stream(stream)>>>(
+        cs2::make_dev_params<double>(*params, dt), level_tables_dev, f, g, cs2::nl_streams<double>(f, dims->ncol_stride),
+        dims->ncol, dims->ncol_stride, dims->nlev, factor, ignore_supsat);
+  } else {
+    const auto f = cs2::make_nl_fields<float>(*traj), g = cs2::make_nl_fields<float>(*pert_out);
+    tl_inc_kernel<float><<<grid, kWideBlock, 0, as_stream(stream)>>>(
+        cs2::make_dev_params<float>(*params, dt), level_tables_dev, f, g, cs2::nl_streams<float>(f, dims->ncol_stride),
+        dims->ncol, dims->ncol_stride, dims->nlev, float(factor), ignore_supsat);
+  }
+  return check_cuda(cudaGetLastError(), "cloudsc2_tl_increment launch");
 }
 
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {

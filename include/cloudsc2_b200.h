@@ -170,6 +170,19 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt,
            void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused "state_increment" + "cloudsc2_tl": TL with the perturbation of every input formed in registers as
+ * factor * input (common/_stencils/state_increment.py:60-80; supsat_i = 0 when ignore_supsat != 0), which is
+ * how both validation harnesses build their perturbation (tangent_linear/validation.py:158-162,
+ * adjoint/validation.py:136-140).  `traj` as in cs2_tl; of `pert_out` only the 10 out_* members are used.
+ * The perturbations are bit-identical to cs2_state_increment's (products rounded on their own); the results equal
+ * cs2_state_increment followed by cs2_tl up to FMA contraction (field-scaled difference ~1e-14, within the 1e-12 parity tolerance), at 36 instead of
+ * 84 field passes through HBM.
+ * ------------------------------------------------------------------------------------- */
+int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt,
+                     const void* level_tables_dev, const cs2_nl_fields* traj,
+                     const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * "cloudsc2_ad" stencil -- adjoint/_stencils/cloudsc2.py:24-996, called from
  * Cloudsc2AD.array_call (adjoint/microphysics.py:159-238).
  *   traj : NL inputs + trajectory outputs (clc, covptot, fluxes, tendencies).

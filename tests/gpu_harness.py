@@ -103,10 +103,10 @@ def run_taylor(block: str = "base", dtype=np.float64, ncol: int = 100, fused: bo
     return tt, norms
 
 
-def run_symmetry(block: str = "base", dtype=np.float64, ncol: int = 100, ad_predicates: str = "tl"):
+def run_symmetry(block: str = "base", dtype=np.float64, ncol: int = 100, ad_predicates: str = "tl", fused: bool = False):
     cfg, grid, state = make_grid_state(block, dtype, ncol)
     p = iox.ifs_defaults()
     st = SymmetryTest(grid, 0.01, 1, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"],
-                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates)
+                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates, fused=fused)
     passed = st(state, timedelta(seconds=H.DT), verbose=False)
     return st, passed

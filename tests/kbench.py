@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--precision", default="double")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--fused", action="store_true")
     args = ap.parse_args()
     dtype = np.float64 if args.precision == "double" else np.float32
     es = np.dtype(dtype).itemsize
@@ -82,6 +83,18 @@ def main():
             ms = time_call(fn, args.reps)
             gbs = ELEMS[name] * es * ncol / ms / 1e6
             res[name] = {"ms": round(ms, 4), "Mcol_s": round(ncol / ms / 1e3, 2), "GBs": round(gbs, 1), "frac": round(gbs / 6541.8, 4)}
+        if args.fused:  # opt-in fused path: state_increment + TL in one sweep
+            from cloudsc2_b200.physics.tangent_linear.microphysics import IncrementedCloudsc2TL
+
+            tli = IncrementedCloudsc2TL(grid, 0.01, True, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"],
+                                        p["yrncl"], p["yrphnc"], gt4py_config=cfg)
+            for name, fn in (
+                ("increment+tl (2 launches)", lambda: (st.state_increment(state, out=st.state_i),
+                                                       st.cloudsc2_tl(state, dt, out_tendencies=st.tends_tl,
+                                                                      out_diagnostics=st.diags_tl))),
+                ("tl_increment fused", lambda: tli(state, dt, out_tendencies=st.tends_tl, out_diagnostics=st.diags_tl)),
+            ):
+                res[name] = {"ms": round(time_call(fn, args.reps), 4)}
         print(json.dumps(res), flush=True)
         del st, st_ck, nl, sat, state, tn, dg
         torch.cuda.empty_cache()
