@@ -430,3 +430,25 @@ def test_tma_bulk_copy_variant_of_nl_matches_oracle():
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CS2_NL_BULK="1"), capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and "BULK_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+def test_two_warp_split_variant_of_nl_matches_oracle(dtype_name):
+    """`CS2_NL_SPLIT=1` selects the two-warps-per-column NL kernel (level_nl_a / level_nl_b handed over through shared memory;
+    measured alternative, not the default): same results as the oracle, including a ragged last CTA."""
+    import subprocess
+    import sys
+
+    tol = "1e-12" if dtype_name == "float64" else "1e-5"
+    code = (
+        "import sys, numpy as np; sys.path[:0]=[%r, %r, %r];"
+        "import helpers as H, gpu_harness as G;"
+        "dt=np.%s;"
+        "out=G.run_components(block='base', dtype=dt, ncol=1001, nl_only=True);"
+        "P=H.externals(); s=H.with_diagnostics(H.make_state('base', dt, 1001), P);"
+        "tn,dg=H.onp.cloudsc2_nl(s,H.DT,P);"
+        "H.assert_fields_close(out['tends_nl'],tn,%s); H.assert_fields_close(out['diags_nl'],dg,%s); print('SPLIT_OK')"
+    ) % (os.path.join(H.ROOT, "tests"), H.ROOT, H.PKG_DIR, dtype_name, tol, tol)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CS2_NL_SPLIT="1"), capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "SPLIT_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
