@@ -172,19 +172,16 @@ CS2_HD void column_nl_split(const DevParams<R>& p, const LevelTables<R>& tab, co
 // ---------------------------------------------------------------------------------------
 // TL column: trajectory and perturbation together
 // ---------------------------------------------------------------------------------------
-template <class R>
+// EVAP: LEVAPLS2 or LDRAIN1D (the precipitation-evaporation branch and its tangent, level_fwd_tl only)
+template <class R, bool EVAP = false>
 CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f, const NLFields<R>& g,
                       int64_t S, int nlev, int64_t i) {
-#if defined(CS2_TL_SPLIT)
-  using C = Cfg<false, true>;
-#endif
+  using C = Cfg<EVAP, true>;
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, S, i);
   const int ncand = tab.nw + 1;
 
   Carry<R> c{R(0), R(0), R(0)}, ci{R(0), R(0), R(0)};
-#if defined(CS2_TL_SPLIT)
-  const R aph_s = f.aph[int64_t(nlev) * S + i];
-#endif
+  const R aph_s = f.aph[int64_t(nlev) * S + i], aph_s_i = g.aph[int64_t(nlev) * S + i];
   R aph0 = f.aph[i], aph0_i = g.aph[i];
   // half level 0 (TL :757-765)
   f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
@@ -199,8 +196,9 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     Trans<R, 0> x;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
+    (void)aph_s_i;
 #else
-    level_fwd_tl<R>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, c, ci, o, oi);
+    level_fwd_tl<R, C>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, aph_s_i, c, ci, o, oi);
 #endif
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
     const uint32_t offn = off + uint32_t(S);

@@ -236,20 +236,19 @@ inline Streams<R, 2 * I_NL> tl_streams(const NLFields<R>& f, const NLFields<R>& 
 // INC: fused "state_increment" + "cloudsc2_tl" (cs2_tl_increment): the perturbation of every input is fac * input
 // (common/_stencils/state_increment.py:60-80; supsat_i = 0 with IGNORE_SUPSAT), formed in registers -- only the 16
 // trajectory inputs are streamed.
-template <class R, int BLOCK, bool INC = false>
+template <class R, int BLOCK, bool INC = false, bool EVAP = false>
 __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const NLFields<R>& g, const Streams<R, (INC ? 1 : 2) * I_NL>& in_s,
                                               Ring<R, (INC ? 1 : 2) * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
                                               bool valid, R fac = R(0), bool ignore_supsat = false) {
-  using C = Cfg<false, true>;
+  using C = Cfg<EVAP, true>;
   ring_issue(ring, in_s, i);
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   const int ncand = tab.nw + 1;
 
   Carry<R> c{R(0), R(0), R(0)}, ci{R(0), R(0), R(0)};
-#if defined(CS2_TL_SPLIT)
   const R aph_s = f.aph[uint32_t(nlev) * S + i];
-#endif
+  const R aph_s_i = EVAP ? (INC ? mul_rn(fac, aph_s) : g.aph[uint32_t(nlev) * S + i]) : R(0);
   R aph0 = f.aph[i], aph0_i = INC ? mul_rn(fac, aph0) : g.aph[i];
   if (valid) {  // half level 0 (TL :757-765)
     f.fplsl[i] = R(0); f.fplsn[i] = R(0); f.fhpsl[i] = R(0); f.fhpsn[i] = R(0);
@@ -279,8 +278,9 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
     Trans<R, 0> x;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
     level_tl<R>(p, in, d, tr, ci, oi);
+    (void)aph_s_i;
 #else
-    level_fwd_tl<R>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, c, ci, o, oi);
+    level_fwd_tl<R, C>(p, in, d, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, aph_s_i, c, ci, o, oi);
 #endif
     if (valid) {
       const uint32_t offn = off + S;

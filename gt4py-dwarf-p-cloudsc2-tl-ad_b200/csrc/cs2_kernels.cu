@@ -191,11 +191,14 @@ nlp_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__
 #ifndef CS2_TL_MAXNREG
 #define CS2_TL_MAXNREG 128
 #endif
+#ifndef CS2_TL_EVAP_MAXNREG
+#define CS2_TL_EVAP_MAXNREG 168  // the evaporation branch (non-default flags) does not fit 128 registers without spills
+#endif
 #ifndef CS2_AD_MAXNREG
 #define CS2_AD_MAXNREG 240
 #endif
-template <class R>
-__global__ void __maxnreg__(CS2_TL_MAXNREG)
+template <class R, bool EVAP>
+__global__ void __maxnreg__(EVAP ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
@@ -204,12 +207,12 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_tl<R, kWideBlock>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
+  cs2::dev_column_tl<R, kWideBlock, false, EVAP>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 // fused state_increment + TL (cs2_tl_increment)
-template <class R>
-__global__ void __maxnreg__(CS2_TL_MAXNREG)
+template <class R, bool EVAP>
+__global__ void __maxnreg__(EVAP ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
 tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
               const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev, R fac,
@@ -219,7 +222,7 @@ tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_tl<R, kWideBlock, true>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, fac,
+  cs2::dev_column_tl<R, kWideBlock, true, EVAP>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, fac,
                                           ignore_supsat != 0);
 }
 
@@ -477,12 +480,42 @@ int launch_nl_pert(const cs2_dims* d, const cs2_params* P, double dt, const void
   return check_cuda(cudaGetLastError(), "cloudsc2_nl_perturbed launch");
 }
 
-int check_tl_ad_flags(const cs2_params* P, const char* what) {
+template <class R>
+int launch_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
+              const cs2_nl_fields* pert, cudaStream_t st) {
+  const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
+  const auto f = cs2::make_nl_fields<R>(*traj), g = cs2::make_nl_fields<R>(*pert);
+  const auto p = cs2::make_dev_params<R>(*P, dt);
+  const auto ns = cs2::tl_streams<R>(f, g, d->ncol_stride);
+  if (P->LEVAPLS2 || P->LDRAIN1D)
+    tl_kernel<R, true><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev);
+  else
+    tl_kernel<R, false><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev);
+  return check_cuda(cudaGetLastError(), "cloudsc2_tl launch");
+}
+
+template <class R>
+int launch_tl_inc(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
+                  const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat, cudaStream_t st) {
+  const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
+  const auto f = cs2::make_nl_fields<R>(*traj), g = cs2::make_nl_fields<R>(*pert_out);
+  const auto p = cs2::make_dev_params<R>(*P, dt);
+  const auto ns = cs2::nl_streams<R>(f, d->ncol_stride);
+  if (P->LEVAPLS2 || P->LDRAIN1D)
+    tl_inc_kernel<R, true><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor),
+                                                        ignore_supsat);
+  else
+    tl_inc_kernel<R, false><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor),
+                                                         ignore_supsat);
+  return check_cuda(cudaGetLastError(), "cloudsc2_tl_increment launch");
+}
+
+int check_ad_flags(const cs2_params* P, const char* what) {
   if (P->LEVAPLS2 || P->LDRAIN1D)
     return fail(CS2_ERR_UNSUPPORTED,
                 std::string(what) + ": the precipitation-evaporation branch (LEVAPLS2 / LDRAIN1D) is not implemented "
-                                    "for TL/AD; the reference's own TL/AD of that branch are mutually inconsistent "
-                                    "(see DESIGN.md)");
+                                    "for AD (NL and TL support it); the reference's own TL and AD of that branch are mutually "
+                                    "inconsistent (see DESIGN.md)");
   return CS2_OK;
 }
 
@@ -652,21 +685,9 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
   if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl: params or level tables NULL");
   if (int rc = check_nl_fields(traj, "cloudsc2_tl trajectory fields")) return rc;
   if (int rc = check_nl_fields(pert, "cloudsc2_tl perturbation fields")) return rc;
-  if (int rc = check_tl_ad_flags(params, "cloudsc2_tl")) return rc;
   if (dims->ncol == 0) return CS2_OK;
-  const unsigned grid = (unsigned)((dims->ncol + kWideBlock - 1) / kWideBlock);
-  if (dims->dtype == CS2_F64) {
-    const auto f = cs2::make_nl_fields<double>(*traj), g = cs2::make_nl_fields<double>(*pert);
-    tl_kernel<double><<<grid, kWideBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<double>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<double>(f, g, dims->ncol_stride),
-        dims->ncol, dims->ncol_stride, dims->nlev);
-  } else {
-    const auto f = cs2::make_nl_fields<float>(*traj), g = cs2::make_nl_fields<float>(*pert);
-    tl_kernel<float><<<grid, kWideBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<float>(*params, dt), level_tables_dev, f, g, cs2::tl_streams<float>(f, g, dims->ncol_stride),
-        dims->ncol, dims->ncol_stride, dims->nlev);
-  }
-  return check_cuda(cudaGetLastError(), "cloudsc2_tl launch");
+  return dims->dtype == CS2_F64 ? launch_tl<double>(dims, params, dt, level_tables_dev, traj, pert, as_stream(stream))
+                                : launch_tl<float>(dims, params, dt, level_tables_dev, traj, pert, as_stream(stream));
 }
 
 int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
@@ -678,21 +699,10 @@ int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, 
   if (!pert_out) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl_increment: perturbation outputs NULL");
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(pert_out) + 16, 10, "cloudsc2_tl_increment perturbation outputs"))
     return rc;
-  if (int rc = check_tl_ad_flags(params, "cloudsc2_tl_increment")) return rc;
   if (dims->ncol == 0) return CS2_OK;
-  const unsigned grid = (unsigned)((dims->ncol + kWideBlock - 1) / kWideBlock);
-  if (dims->dtype == CS2_F64) {
-    const auto f = cs2::make_nl_fields<double>(*traj), g = cs2::make_nl_fields<double>(*pert_out);
-    tl_inc_kernel<double><<<grid, kWideBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<double>(*params, dt), level_tables_dev, f, g, cs2::nl_streams<double>(f, dims->ncol_stride),
-        dims->ncol, dims->ncol_stride, dims->nlev, factor, ignore_supsat);
-  } else {
-    const auto f = cs2::make_nl_fields<float>(*traj), g = cs2::make_nl_fields<float>(*pert_out);
-    tl_inc_kernel<float><<<grid, kWideBlock, 0, as_stream(stream)>>>(
-        cs2::make_dev_params<float>(*params, dt), level_tables_dev, f, g, cs2::nl_streams<float>(f, dims->ncol_stride),
-        dims->ncol, dims->ncol_stride, dims->nlev, float(factor), ignore_supsat);
-  }
-  return check_cuda(cudaGetLastError(), "cloudsc2_tl_increment launch");
+  return dims->dtype == CS2_F64
+             ? launch_tl_inc<double>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, as_stream(stream))
+             : launch_tl_inc<float>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, as_stream(stream));
 }
 
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
@@ -715,7 +725,7 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void
   static_assert(sizeof(cs2_ad_outputs) == 16 * sizeof(void*), "cs2_ad_outputs layout");
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(seeds), 10, "cloudsc2_ad seeds")) return rc;
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(adj), 16, "cloudsc2_ad adjoint outputs")) return rc;
-  if (int rc = check_tl_ad_flags(params, "cloudsc2_ad")) return rc;
+  if (int rc = check_ad_flags(params, "cloudsc2_ad")) return rc;
   if (mode != CS2_AD_RECOMPUTE && mode != CS2_AD_CHECKPOINT) return fail(CS2_ERR_BAD_DIMS, "cloudsc2_ad: unknown mode");
   if (!workspace_dev || workspace_bytes < cs2_ad_workspace_bytes(dims, params, mode))
     return fail(CS2_ERR_WORKSPACE, "cloudsc2_ad: workspace missing or too small");

@@ -38,9 +38,14 @@ CS2_HD void adj_step_fwd_tl(const DevParams<R>& p, R rap, R ap_i, R z3, R z4, R 
   q_i -= cond_i;
 }
 
-template <class R>
+// C::EVAP (LEVAPLS2 or LDRAIN1D): also the precipitation-evaporation branch and its tangent, a statement-by-statement
+// restatement of tangent_linear/_stencils/cloudsc2.py:224-230,388-397,525-616 -- including that stencil's `dt**2` in the
+// tangent of the implicit solution (:577-579), where the quotient rule gives `dt`: the reference's TL of this branch is
+// not the derivative of its NL, and the drop-in reproduces the reference.  aph_s / aph_s_i: surface
+// pressure of the column and its perturbation (only read when C::EVAP).
+template <class R, class C = Cfg<false, true>>
 CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const LevelIn<R>& d, R scalm, R crh2, bool conv_ok,
-                         Carry<R>& c, Carry<R>& ci, LevelOut<R>& o, LevelOut<R>& oi) {
+                         R aph_s, R aph_s_i, Carry<R>& c, Carry<R>& ci, LevelOut<R>& o, LevelOut<R>& oi) {
   const R one = R(1), zero = R(0);
   // ---- first guess (TL :149-156)
   const R t0 = in.t + p.dt * in.tnd_t;
@@ -91,6 +96,14 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
   const R cor_i = p.RETV * esdp_i * cor * cor;
   const R dqsdtemp = fac * cor * in.qsat;
   const R dqsdtemp_i = fac_i * cor * in.qsat + fac * cor_i * in.qsat + fac * cor * d.qsat;
+  R corqs = one, corqs_i = zero, qlim = zero, qlim_i = zero;
+  if (C::EVAP) {  // (TL :216-230)
+    corqs = one + p.cons3 * dqsdtemp;
+    corqs_i = p.cons3 * dqsdtemp_i;
+    const bool qclip = q0 > in.qsat;
+    qlim = qclip ? in.qsat : q0;
+    qlim_i = qclip ? d.qsat : q_i;
+  }
 
   // ---- critical humidity (TL :255-265)
   const bool ice = t0 < p.RTICE;
@@ -182,6 +195,15 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
     c.covptot = clc;
     ci.covptot = clc_i;
   }
+  R covpclr = zero, covpclr_i = zero;
+  if (C::EVAP) {
+    covpclr = c.covptot - clc;
+    covpclr_i = ci.covptot - clc_i;
+    if (covpclr < zero) {
+      covpclr = zero;
+      covpclr_i = zero;
+    }
+  }
 
   // ---- melting of incoming snow (TL :399-427)
   R rfln = c.rfl, sfln = c.sfl, rfln_i = ci.rfl, sfln_i = ci.sfl;
@@ -248,14 +270,79 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
     rfln_i += dr_i;
   }
 
+  // ---- precipitation evaporation (TL :525-616) -- dead unless LEVAPLS2 or LDRAIN1D
+  R evapr = zero, evapr_i = zero, evaps = zero, evaps_i = zero;
+  o.covptot = zero;
+  oi.covptot = zero;
+  if (C::EVAP) {
+    const R prtot = rfln + sfln, prtot_i = rfln_i + sfln_i;
+    if (prtot > p.ZEPS2 && covpclr > p.ZEPS2) {
+      // The trajectory statements are written exactly as in level_fwd (IEEE divisions, same association): when all
+      // precipitation evaporates the fluxes must come out as exact zeros like the reference's, because `sfl != 0`
+      // decides the melting branch of the level below.  Only the tangent statements use shared reciprocals.
+      const R rcov = rcp(c.covptot);
+      R preclr = prtot * covpclr / c.covptot;
+      R preclr_i = (prtot_i * covpclr + prtot * covpclr_i) * rcov - prtot * covpclr * ci.covptot * rcov * rcov;
+      // humidity in the moistest covpclr region
+      const R omc = one - clc;
+      const R romc2 = rcp(omc * omc);
+      const R dqs = in.qsat - qlim;
+      const R qe = in.qsat - dqs * covpclr / (omc * omc);
+      const R qe_i = d.qsat - (d.qsat * covpclr - qlim_i * covpclr + dqs * covpclr_i) * romc2 -
+                     R(2) * dqs * covpclr * clc_i * romc2 * rcp(omc);
+      const R tmp6 = sqrt_(in.ap / aph_s);
+      const R rcovpclr = rcp(covpclr);
+      const R beta = p.RG * p.RPECONS * pow_(tmp6 / R(0.00509) * preclr / covpclr, R(0.5777));
+      const R beta_i =
+          R(0.5777) * p.RG * p.RPECONS / R(0.00509) * pow_(R(0.00509) * covpclr / (tmp6 * preclr), R(0.4223)) *
+          ((tmp6 * preclr_i + R(0.5) * preclr * d.ap / tmp6 - R(0.5) * preclr * tmp6 * aph_s_i / aph_s) * rcovpclr -
+           tmp6 * preclr * covpclr_i * rcovpclr * rcovpclr);
+      // implicit solution; `dt * dt` is the reference's (TL :577-579), the derivative of b would have `dt`
+      const R rden = rcp(one + p.dt * beta * corqs);
+      const R b = p.dt * beta * (in.qsat - qe) / (one + p.dt * beta * corqs);
+      const R b_i = p.dt * (beta_i * (in.qsat - qe) + beta * (d.qsat - qe_i)) * rden -
+                    p.dt * p.dt * b * (beta_i * corqs + beta * corqs_i) * rden;
+      const R dtgdp = p.dt * p.RG * rdp;
+      const R rdtgdp = rcp(dtgdp);
+      const R dtgdp_i = -p.rgdt * dp_i * rdp * rdp;
+      R dpr = covpclr * b / dtgdp;
+      R dpr_i = (covpclr_i * b + covpclr * b_i) * rdtgdp - covpclr * b * dtgdp_i * rdtgdp * rdtgdp;
+      if (dpr > preclr) {
+        dpr = preclr;
+        dpr_i = preclr_i;
+      }
+      preclr -= dpr;
+      preclr_i -= dpr_i;
+      if (preclr <= zero) {
+        c.covptot = clc;
+        ci.covptot = clc_i;
+      }
+      o.covptot = c.covptot;
+      oi.covptot = ci.covptot;
+      const R rpr = rcp(prtot);
+      evapr = dpr * rfln / prtot;  // warm proportion
+      evapr_i = (dpr_i * rfln + dpr * rfln_i) * rpr - dpr * rfln * prtot_i * rpr * rpr;
+      evaps = dpr * sfln / prtot;  // ice proportion
+      evaps_i = (dpr_i * sfln + dpr * sfln_i) * rpr - dpr * sfln * prtot_i * rpr * rpr;
+      rfln -= evapr;
+      rfln_i -= evapr_i;
+      sfln -= evaps;
+      sfln_i -= evaps_i;
+    }
+  }
+
   // ---- first-guess T and q (TL :618-659)
   const R dlv = lsdcp - lvdcp, dlv_i = lsdcp_i - lvdcp_i;
-  const R dqdt = -(condl + condi) + in.lude * gdp;
-  const R dqdt_i = -(condl_i + condi_i) + d.lude * gdp + in.lude * gdp_i;
-  const R dtdt = lvdcp * condl + lsdcp * condi - (in.lude * ldcp - dlv * rfreeze) * gdp;
+  const R src = C::EVAP ? in.lude + evapr + evaps : in.lude;          // moisture sources per unit gdp
+  const R src_i = C::EVAP ? d.lude + evapr_i + evaps_i : d.lude;
+  const R lev = C::EVAP ? lvdcp * evapr + lsdcp * evaps : zero;       // latent heat of the evaporated precipitation
+  const R lev_i = C::EVAP ? lvdcp_i * evapr + lvdcp * evapr_i + lsdcp_i * evaps + lsdcp * evaps_i : zero;
+  const R dqdt = -(condl + condi) + src * gdp;
+  const R dqdt_i = -(condl_i + condi_i) + src_i * gdp + src * gdp_i;
+  const R dtdt = lvdcp * condl + lsdcp * condi - (lev + in.lude * ldcp - dlv * rfreeze) * gdp;
   const R dtdt_i = lvdcp_i * condl + lvdcp * condl_i + lsdcp_i * condi + lsdcp * condi_i -
-                   (d.lude * ldcp + in.lude * ldcp_i - dlv_i * rfreeze - dlv * rfreeze_i) * gdp -
-                   (in.lude * ldcp - dlv * rfreeze) * gdp_i;
+                   (lev_i + d.lude * ldcp + in.lude * ldcp_i - dlv_i * rfreeze - dlv * rfreeze_i) * gdp -
+                   (lev + in.lude * ldcp - dlv * rfreeze) * gdp_i;
   R t = tmelt + p.dt * dtdt;
   t_i += p.dt * dtdt_i;
   const R qa = q0 + p.dt * dqdt;
@@ -296,14 +383,12 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
   // ---- outputs (TL :705-753)
   o.clc = clc;
   oi.clc = clc_i;
-  o.covptot = zero;
-  oi.covptot = zero;
-  o.tnd_q = -(condl + condi) + in.lude * gdp;
-  oi.tnd_q = -(condl_i + condi_i) + d.lude * gdp + in.lude * gdp_i;
-  o.tnd_t = lvdcp * condl + lsdcp * condi - (in.lude * ldcp - dlv * rfreeze) * gdp;
+  o.tnd_q = -(condl + condi) + src * gdp;
+  oi.tnd_q = -(condl_i + condi_i) + src_i * gdp + src * gdp_i;
+  o.tnd_t = lvdcp * condl + lsdcp * condi - (lev + in.lude * ldcp - dlv * rfreeze) * gdp;
   oi.tnd_t = lvdcp_i * condl + lvdcp * condl_i + lsdcp_i * condi + lsdcp * condi_i -
-             (d.lude * ldcp + in.lude * ldcp_i - dlv_i * rfreeze - dlv * rfreeze_i) * gdp -
-             (in.lude * ldcp - dlv * rfreeze) * gdp_i;
+             (lev_i + d.lude * ldcp + in.lude * ldcp_i - dlv_i * rfreeze - dlv * rfreeze_i) * gdp -
+             (lev + in.lude * ldcp - dlv * rfreeze) * gdp_i;
   o.tnd_ql = (qlwc - ql0) * p.rdt;
   oi.tnd_ql = (qlwc_i - ql_i) * p.rdt;
   o.tnd_qi = (qiwc - qi0) * p.rdt;

@@ -49,8 +49,12 @@ void run_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* table
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f), ng = cs2::make_nl_fields<R>(*g);
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < d->ncol; ++i) cs2::column_tl<R>(p, tab, nf, ng, d->ncol_stride, d->nlev, i);
+  for (int64_t i = 0; i < d->ncol; ++i) {
+    if (evap) cs2::column_tl<R, true>(p, tab, nf, ng, d->ncol_stride, d->nlev, i);
+    else cs2::column_tl<R, false>(p, tab, nf, ng, d->ncol_stride, d->nlev, i);
+  }
 }
 
 template <class R>

@@ -67,7 +67,10 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
         return out
 
     st = SymmetryTest(grid, 0.01, 1, lphylin, ldrain1d, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"],
-                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates, ad_trajectory=ad_trajectory)
+                      p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates, ad_trajectory=ad_trajectory,
+                      fused=bool(flags.get("fused", False)))
+    if "ignore_supsat" in flags:  # the symmetry harness ignores supsat; the Taylor harness does not
+        st.state_increment = StateIncrement(grid, 0.01, ignore_supsat=bool(flags["ignore_supsat"]), gt4py_config=cfg)
     # run the pipeline step by step to keep host copies of the TL outputs before AD consumes them
     st.diags_sat = st.saturation(state, out=st.diags_sat)
     state.update(st.diags_sat)
@@ -76,6 +79,8 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
     out["state_i"] = to_host(st.state_i)
     st.tends_tl, st.diags_tl = st.cloudsc2_tl(state, dt, out_tendencies=st.tends_tl, out_diagnostics=st.diags_tl)
     out["tends_tl"], out["diags_tl"] = to_host(st.tends_tl), to_host(st.diags_tl)
+    if flags.get("tl_only"):
+        return out
     norm1 = st.get_norm1(st.tends_tl, st.diags_tl)
     st.add_tendencies_to_state(state, st.tends_tl)
     state.update(st.diags_tl)

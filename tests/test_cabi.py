@@ -65,7 +65,13 @@ def test_argument_validation_without_gpu():
     evap = _lib.make_params(H.externals(LEVAPLS2=True))
     for name, _ in _lib.NLFields._fields_:
         setattr(f, name, p)
-    assert lib.cs2_tl(C.byref(ok), C.byref(evap), 3600.0, p, C.byref(f), C.byref(f), None) == -4  # UNSUPPORTED
+    seeds, outs = _lib.ADSeeds(), _lib.ADOutputs()
+    for st in (seeds, outs):
+        for name, _ in st._fields_:
+            setattr(st, name, p)
+    rc = lib.cs2_ad(C.byref(ok), C.byref(evap), 3600.0, p, C.byref(f), C.byref(seeds), C.byref(outs), p, 1 << 30,
+                    _lib.CS2_AD_RECOMPUTE, None)
+    assert rc == -4  # CS2_ERR_UNSUPPORTED: the evaporation branch exists for NL and TL, not for AD
     assert b"evaporation" in lib.cs2_last_error()
     empty = _lib.Dims(0, 32, 4, _lib.CS2_F64)  # zero columns: nothing to launch, no GPU needed
     assert lib.cs2_saturation(C.byref(empty), C.byref(params), p, p, p, None) == 0

@@ -344,6 +344,26 @@ def test_fused_symmetry_test_equals_unfused():
     assert st_b.norm3_max < max(1e3, 4 * st_a.norm3_max)
 
 
+@pytest.mark.parametrize("flags", [dict(levapls2=True), dict(ldrain1d=True)])
+@pytest.mark.parametrize("lregcl", [True, False])
+def test_tl_evaporation_branch_matches_oracle(flags, lregcl):
+    """TL with LEVAPLS2 / LDRAIN1D (precipitation-evaporation branch incl. its tangent) against the oracle's literal
+    restatement of tangent_linear/_stencils/cloudsc2.py:525-616; ragged column count; AD of the branch is refused."""
+    from cloudsc2_b200._lib import CUDAExtensionError
+
+    ncol = 333
+    out = gh().run_components(block="base", dtype=np.float64, ncol=ncol, lregcl=lregcl, tl_only=True, ignore_supsat=False, **flags)
+    P = H.externals(LREGCL=lregcl, LEVAPLS2=flags.get("levapls2", False), LDRAIN1D=flags.get("ldrain1d", False))
+    s = H.with_diagnostics(H.make_state("base", np.float64, ncol), P)
+    s.update(H.onp.state_increment(s, 0.01))
+    rt, rd = H.onp.cloudsc2_tl(s, H.DT, P)
+    assert np.count_nonzero(rd["f_covptot_i"]) > 0
+    got = {**out["tends_tl"], **out["diags_tl"]}
+    H.assert_close_except_total_evaporation_knife_edges(got, {**rt, **rd}, 1e-12, max_columns=max(2, ncol // 50))
+    with pytest.raises(CUDAExtensionError, match="evaporation"):
+        gh().run_components(block="base", dtype=np.float64, ncol=64, **flags)
+
+
 def test_empty_grid_is_a_no_op():
     """nx = 0: nothing is launched, nothing fails."""
     out = gh().run_components(block="base", dtype=np.float64, ncol=0, nl_only=True)
@@ -432,23 +452,20 @@ def test_tma_bulk_copy_variant_of_nl_matches_oracle():
     assert res.returncode == 0 and "BULK_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
 
 
-@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
-def test_two_warp_split_variant_of_nl_matches_oracle(dtype_name):
+def test_two_warp_split_variant_of_nl_matches_oracle():
     """`CS2_NL_SPLIT=1` selects the two-warps-per-column NL kernel (level_nl_a / level_nl_b handed over through shared memory;
     measured alternative, not the default): same results as the oracle, including a ragged last CTA."""
     import subprocess
     import sys
 
-    tol = "1e-12" if dtype_name == "float64" else "1e-5"
     code = (
         "import sys, numpy as np; sys.path[:0]=[%r, %r, %r];"
         "import helpers as H, gpu_harness as G;"
-        "dt=np.%s;"
-        "out=G.run_components(block='base', dtype=dt, ncol=1001, nl_only=True);"
-        "P=H.externals(); s=H.with_diagnostics(H.make_state('base', dt, 1001), P);"
+        "out=G.run_components(block='base', dtype=np.float64, ncol=1001, nl_only=True);"
+        "P=H.externals(); s=H.with_diagnostics(H.make_state('base', np.float64, 1001), P);"
         "tn,dg=H.onp.cloudsc2_nl(s,H.DT,P);"
-        "H.assert_fields_close(out['tends_nl'],tn,%s); H.assert_fields_close(out['diags_nl'],dg,%s); print('SPLIT_OK')"
-    ) % (os.path.join(H.ROOT, "tests"), H.ROOT, H.PKG_DIR, dtype_name, tol, tol)
+        "H.assert_fields_close(out['tends_nl'],tn,1e-12); H.assert_fields_close(out['diags_nl'],dg,1e-12); print('SPLIT_OK')"
+    ) % (os.path.join(H.ROOT, "tests"), H.ROOT, H.PKG_DIR)
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CS2_NL_SPLIT="1"), capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and "SPLIT_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]

@@ -66,6 +66,23 @@ def test_twin_tl(block, dtype, lregcl):
     H.assert_fields_close(td, rd, tol_d, "TL diagnostics: ")
 
 
+@pytest.mark.parametrize("flags", [dict(LEVAPLS2=True), dict(LDRAIN1D=True)])
+@pytest.mark.parametrize("lregcl", [True, False])
+@pytest.mark.parametrize("block", ["base", "cold"])
+def test_twin_tl_evaporation_branch(block, lregcl, flags):
+    """TL with the precipitation-evaporation branch (LEVAPLS2 / LDRAIN1D) against the oracle's literal restatement of
+    tangent_linear/_stencils/cloudsc2.py:525-616 (the branch is exercised: f_covptot and f_covptot_i are non-zero)."""
+    P = H.externals(LREGCL=lregcl, **flags)
+    s = H.with_diagnostics(H.make_state(block), P)
+    s.update(H.onp.state_increment(s, 0.01))
+    rt, rd = H.onp.cloudsc2_tl(s, H.DT, P)
+    assert np.count_nonzero(rd["f_covptot"]) > 0
+    if block == "base":
+        assert np.count_nonzero(rd["f_covptot_i"]) > 0
+    tt, td = H.twin_tl(s, H.DT, P)
+    H.assert_close_except_total_evaporation_knife_edges({**tt, **td}, {**rt, **rd}, 1e-12, max_columns=2, what=f"TL {flags}: ")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("block,predicates", [("base", "tl"), ("base", "reference"), ("cold", "tl")])
 def test_twin_ad(block, predicates, dtype):
