@@ -46,13 +46,15 @@ def core(config, io_config, fused=False):
 @click.option("--output-csv-file", type=str, default=None)
 @click.option("--input-file", type=str, default=None)
 @click.option("--fused/--unfused", is_flag=True, default=False, help="fuse PerturbedState into the NL kernel and StateIncrement into the TL kernel (same results)")
-def main(enable_checks, num_cols, num_runs, precision, host_alias, output_csv_file, input_file, fused):
+@click.option("--fused-sums", is_flag=True, default=False,
+              help="one sweep per factor: increment, perturbation, NL and the field sums fused (same norms up to summation order)")
+def main(enable_checks, num_cols, num_runs, precision, host_alias, output_csv_file, input_file, fused, fused_sums):
     config = (DEFAULT_CONFIG.with_precision(precision).with_checks(enable_checks).with_num_cols(num_cols or 100)
               .with_num_runs(num_runs))
     if input_file:
         config.input_file = input_file
     io_config = DEFAULT_IO_CONFIG.with_output_csv_file(output_csv_file).with_host_name(host_alias)
-    raise SystemExit(0 if core(config, io_config, fused) else 1)
+    raise SystemExit(0 if core(config, io_config, "sums" if fused_sums else fused) else 1)
 
 
 if __name__ == "__main__":

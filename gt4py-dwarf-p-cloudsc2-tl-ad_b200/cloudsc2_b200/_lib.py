@@ -122,6 +122,12 @@ SIGNATURES = {
             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
         ],
     ),
+    "cs2_taylor_nl_scratch_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "cs2_taylor_nl_sums": (
+        C.c_int,
+        [C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.c_double, C.c_int32, C.c_double,
+         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "cs2_symmetry_norms": (
         C.c_int,
         [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p],

@@ -248,6 +248,37 @@ class Cloudsc2NLPerturbedStencil(StencilObject):
                        "cs2_nl_perturbed")
 
 
+@stencil_collection("cloudsc2_nl_taylor_sums")
+class Cloudsc2NLTaylorSumsStencil(StencilObject):
+    """One factor of the Taylor test in one sweep: `state_increment(f1)` -> `perturbed_state(f2)` -> `cloudsc2_nl` and the
+    field sums of get_field_norm (tangent_linear/validation.py:158-176,252-261) -> cs2_taylor_nl_sums.  `in_*` = base state,
+    `out_*` = the UNPERTURBED NL outputs (read); `sums` = fp64 device tensor [10][2], SUM(F_p - F_nl) is added to [:, 0]."""
+
+    def __init__(self, externals: Dict[str, Any], gt4py_config: Any = None) -> None:
+        super().__init__(externals, gt4py_config)
+        self._scratch: Optional[torch.Tensor] = None
+
+    def __call__(self, *, in_eta, dt, f1, f2, sums, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None,
+                 **fields):
+        ref = fields["in_ap"]
+        dims = self._dims(ref, "in_ap")
+        self._check_domain(domain, dims.ncol, dims.nlev + 1)
+        f = _nl_struct(self, fields, dims)
+        tables = self._level_tables(in_eta, dims.nlev, dims, ref.device)
+        nbytes = max(16, self.lib.cs2_taylor_nl_scratch_bytes(C.byref(dims)))
+        if self._scratch is None or self._scratch.numel() < nbytes or self._scratch.device != ref.device:
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
+        assert sums.dtype == torch.float64 and sums.numel() >= 20 and sums.device == ref.device and sums.is_contiguous()
+        with self._Timer(self, exec_info, ref.device):
+            _lib.check(
+                self.lib.cs2_taylor_nl_sums(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(), C.byref(f),
+                                            float(f1), int(bool(self.externals.get("IGNORE_SUPSAT", False))), float(f2),
+                                            sums.data_ptr(), self._scratch.data_ptr(), self._scratch.numel(),
+                                            self._stream(ref)),
+                "cs2_taylor_nl_sums",
+            )
+
+
 @stencil_collection("cloudsc2_tl")
 class Cloudsc2TLStencil(StencilObject):
     """tangent_linear/_stencils/cloudsc2.py:23-774 -> cs2_tl"""

@@ -90,3 +90,33 @@ class PerturbedCloudsc2NL(Cloudsc2NL):
             origin=(0, 0, 0), domain=self.computational_grid.grids[I, J, K - 1 / 2].shape,
             validate_args=self.gt4py_config.validate_args, exec_info=self.gt4py_config.exec_info,
         )
+
+
+class TaylorCloudsc2NL(Cloudsc2NL):
+    """`StateIncrement(factor1)` -> `PerturbedState(factor2)` -> `Cloudsc2NL` -> field sums of the Taylor test, as ONE
+    sweep: the perturbed NL outputs are compared with the unperturbed ones level by level and only the ten sums
+    SUM(F_p - F_nl) leave the kernel (tangent_linear/validation.py:158-176,252-261).  Not in the reference; the opt-in
+    fast path `TaylorTest(fused="sums")`.  Call: `comp(state, timestep, tends_nl, diags_nl, sums)` with the unperturbed
+    NL outputs and an fp64 device tensor [10][2]; adds to sums[:, 0] in the field order of TaylorTest.get_norm."""
+
+    def __init__(self, computational_grid, factor1, factor2, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                 yrecldp_params, yrephli_params, yrphnc_params, *, ignore_supsat=False, enable_checks=True, gt4py_config):
+        super().__init__(computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params,
+                         yrephli_params, yrphnc_params, enable_checks=enable_checks, gt4py_config=gt4py_config)
+        self.f1 = gt4py_config.dtypes.float(factor1)
+        self.f2 = gt4py_config.dtypes.float(factor2)
+        externals = dict(self.cloudsc2.externals, IGNORE_SUPSAT=bool(ignore_supsat))
+        self.cloudsc2_taylor = self.compile_stencil("cloudsc2_nl_taylor_sums", externals)
+
+    def __call__(self, state, timestep, tends_nl, diags_nl, sums):  # noqa: D102 - not a tendency component call
+        raw = lambda fld: getattr(fld, "data", fld)  # noqa: E731 - Field -> logical (nx, 1, nz+1) view, like the base class
+        kwargs = {f"in_{n}": raw(state[f"f_{n}"]) for n in NL_INPUTS}
+        kwargs.update({f"out_{n}": raw(diags_nl[f"f_{n}"]) for n in NL_DIAGNOSTICS})
+        kwargs.update({f"out_tnd_{n}": raw(tends_nl[f"f_{n}"]) for n in NL_TENDENCIES})
+        self.cloudsc2_taylor(
+            **kwargs, in_eta=raw(state["f_eta"]), f1=self.f1, f2=self.f2, sums=sums,
+            dt=self.gt4py_config.dtypes.float(timestep.total_seconds()), origin=(0, 0, 0),
+            domain=self.computational_grid.grids[I, J, K - 1 / 2].shape,
+            validate_args=self.gt4py_config.validate_args, exec_info=self.gt4py_config.exec_info,
+        )
+        return sums

@@ -17,7 +17,7 @@ from ...framework.timing import timing
 from ...reductions import TaylorSums
 from ..common.increment import PerturbedState, StateIncrement
 from ..common.saturation import Saturation
-from ..nonlinear.microphysics import Cloudsc2NL, PerturbedCloudsc2NL
+from ..nonlinear.microphysics import Cloudsc2NL, PerturbedCloudsc2NL, TaylorCloudsc2NL
 from .microphysics import Cloudsc2TL, IncrementedCloudsc2TL
 
 TEND_NAMES = ("f_t", "f_q", "f_ql", "f_qi")
@@ -30,7 +30,10 @@ class TaylorTest:
                  fused=False):
         """`fused=True` replaces each PerturbedState -> Cloudsc2NL pair of the loop by one PerturbedCloudsc2NL call
         (bit-identical fields, 42 instead of 74 field passes per factor; `state_p` is then not materialised) and
-        lets the TL sweep form its perturbation factor1 * state itself (IncrementedCloudsc2TL: 16 fewer field reads)."""
+        lets the TL sweep form its perturbation factor1 * state itself (IncrementedCloudsc2TL: 16 fewer field reads).
+        `fused="sums"` goes one step further: per factor ONE sweep forms the increment and the perturbation in registers,
+        evaluates NL and accumulates SUM(F_nl_p - F_nl) per field (TaylorCloudsc2NL, 26 instead of 62 field passes);
+        `state_p`, `tends_nl_p` and `diags_nl_p` are then not produced.  Same norms up to summation order."""
         self.fused = fused
         self.f1 = factor1
         self.f2s = tuple(factor2s)
@@ -48,7 +51,11 @@ class TaylorTest:
         self.perturbed_states = [PerturbedState(computational_grid, f2, **kw) for f2 in self.f2s]
         self.perturbed_nls = [PerturbedCloudsc2NL(computational_grid, f2, lphylin, ldrain1d, yoethf_params, yomcst_params,
                                                   yrecldp_params, yrephli_params, yrphnc_params, **kw)
-                              for f2 in self.f2s] if fused else []
+                              for f2 in self.f2s] if fused and fused != "sums" else []
+        # fused="sums": one sweep per factor (increment + perturbation + NL + the field sums), nothing else reaches HBM
+        self.taylor_nls = [TaylorCloudsc2NL(computational_grid, factor1, f2, lphylin, ldrain1d, yoethf_params, yomcst_params,
+                                            yrecldp_params, yrephli_params, yrphnc_params, **kw)
+                           for f2 in self.f2s] if fused == "sums" else []
         self.diags_nl: Dict[str, Any] = {}
         self.diags_nl_p: Dict[str, Any] = {}
         self.diags_sat: Dict[str, Any] = {}
@@ -74,8 +81,9 @@ class TaylorTest:
             self.tends_nl, self.diags_nl = self.cloudsc2_nl(
                 state, timestep, out_tendencies=self.tends_nl, out_diagnostics=self.diags_nl
             )
-            self.state_i = self.state_increment(state, out=self.state_i)
-            state.update(self.state_i)
+            if self.fused != "sums":  # in "sums" mode nothing reads the increment: it is formed inside the sweeps
+                self.state_i = self.state_increment(state, out=self.state_i)
+                state.update(self.state_i)
             tl = self.cloudsc2_tl_inc if self.fused else self.cloudsc2_tl  # fused: f_*_i formed in the sweep, not read
             self.tends_tl, self.diags_tl = tl(
                 state, timestep, out_tendencies=self.tends_tl, out_diagnostics=self.diags_tl
@@ -85,6 +93,16 @@ class TaylorTest:
         nfields = len(TEND_NAMES) + len(DIAG_NAMES)
         self._sums = torch.zeros((len(self.f2s), nfields, 2), dtype=torch.float64, device=dev)
         for i, perturbed_state in enumerate(self.perturbed_states):
+            if self.fused == "sums":
+                with timing("run"):
+                    self.taylor_nls[i](state, timestep, self.tends_nl, self.diags_nl, self._sums[i])
+                with timing("norms"):
+                    if i == 0:  # SUM(F_tl_i) does not depend on the factor
+                        c = [self.tends_tl[n + "_i"] for n in TEND_NAMES] + [self.diags_tl[n + "_i"] for n in DIAG_NAMES]
+                        tl_sums = torch.zeros_like(self._sums[0])
+                        self._sums_op(c, c, c, tl_sums.reshape(-1))  # a - b = 0: only SUM(c) is accumulated
+                    self._sums[i, :, 1] = tl_sums[:, 1]
+                continue
             with timing("run"):
                 if self.fused:
                     self.tends_nl_p, self.diags_nl_p = self.perturbed_nls[i](

@@ -220,6 +220,96 @@ __device__ __forceinline__ void dev_column_nl_pert(const DevParams<R>& p, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// One factor of the Taylor test in one sweep (cs2_taylor_nl_sums): NL of the state x + f2 * (f1 * x) -- the
+// StateIncrement(f1) / PerturbedState(f2) / Cloudsc2NL chain of tangent_linear/validation.py:158-176, formed with the same
+// roundings (product rounded on its own, then one FMA) -- compared on the fly with the unperturbed NL outputs F_nl:
+// SUM_k (F_p - F_nl) per output field and column is accumulated in fp64 in per-thread shared-memory slots, so F_p is
+// never written and never re-read.  Streams [0, 16) = x, [16, 26) = F_nl in the order of T_* below.
+// ---------------------------------------------------------------------------------------
+enum { T_TT, T_TQ, T_TQL, T_TQI, T_CLC, T_FHPSL, T_FHPSN, T_FPLSL, T_FPLSN, T_COVPTOT, T_N };
+
+template <class R>
+inline Streams<R, I_NL + T_N> taylor_streams(const NLFields<R>& f, int64_t S) {
+  Streams<R, I_NL + T_N> s;
+  const Streams<R, I_NL> a = nl_streams(f, S);
+  for (int n = 0; n < I_NL; ++n) s.p[n] = a.p[n];
+  s.p[I_NL + T_TT] = f.o_tnd_t; s.p[I_NL + T_TQ] = f.o_tnd_q; s.p[I_NL + T_TQL] = f.o_tnd_ql; s.p[I_NL + T_TQI] = f.o_tnd_qi;
+  s.p[I_NL + T_CLC] = f.clc; s.p[I_NL + T_COVPTOT] = f.covptot;
+  s.p[I_NL + T_FHPSL] = f.fhpsl + S; s.p[I_NL + T_FHPSN] = f.fhpsn + S;  // half-level fields: level k+1
+  s.p[I_NL + T_FPLSL] = f.fplsl + S; s.p[I_NL + T_FPLSN] = f.fplsn + S;
+  return s;
+}
+
+template <class R>
+__device__ __forceinline__ R pert2(R f1, R f2, R x) {
+  return axpy(f2, mul_rn(f1, x), x);  // x + f2 * round(f1 * x): state_increment then perturbed_state
+}
+
+template <class R, class C, int BLOCK>
+__device__ __forceinline__ void dev_column_nl_taylor(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                                     R f1, R f2, bool ignore_supsat,
+                                                     const Streams<R, I_NL + T_N>& in_s, Ring<R, I_NL + T_N, BLOCK>& ring,
+                                                     double (*acc)[BLOCK], uint32_t S, int nlev, uint32_t i, bool valid) {
+  ring_issue(ring, in_s, i);
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int n = 0; n < T_N; ++n) acc[n][t] = 0.0;
+  // tropopause candidate of the perturbed temperature profile (nonlinear/_stencils/cloudsc2.py:106-111)
+  int jsel = 0;
+  {
+    int kprev = -2;
+    R tnext = R(0);
+    for (int j = 0; j < tab.nw; ++j) {
+      const int k = tab.wlev[j];
+      const uint32_t o = uint32_t(k) * S + i;
+      const R tk = (k == kprev + 1) ? tnext : (pert2(f1, f2, f.t[o]) + p.dt * pert2(f1, f2, f.tnd_t[o]));
+      tnext = pert2(f1, f2, f.t[o + S]) + p.dt * pert2(f1, f2, f.tnd_t[o + S]);
+      kprev = k;
+      if (tk > tnext) jsel = j + 1;
+    }
+  }
+  const int ncand = tab.nw + 1;
+  Carry<R> c{R(0), R(0), R(0)};
+  const R aph_s = pert2(f1, f2, f.aph[uint32_t(nlev) * S + i]);
+  R aph0 = pert2(f1, f2, f.aph[i]);
+  for (int k = 0; k < nlev; ++k) {
+    const uint32_t off = uint32_t(k) * S + i;
+    cp_async_wait_all();
+    LevelIn<R> in;
+    ring_read_level(ring, 0, aph0, in);
+    R ref[T_N];
+#pragma unroll
+    for (int n = 0; n < T_N; ++n) ref[n] = ring.v[I_NL + n][t];
+    if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
+    in.ap = pert2(f1, f2, in.ap);         in.aph1 = pert2(f1, f2, in.aph1);     in.lu1 = pert2(f1, f2, in.lu1);
+    in.lude = pert2(f1, f2, in.lude);     in.mfd = pert2(f1, f2, in.mfd);       in.mfu = pert2(f1, f2, in.mfu);
+    in.q = pert2(f1, f2, in.q);           in.qi = pert2(f1, f2, in.qi);         in.ql = pert2(f1, f2, in.ql);
+    in.qsat = pert2(f1, f2, in.qsat);     in.t = pert2(f1, f2, in.t);           in.tnd_q = pert2(f1, f2, in.tnd_q);
+    in.tnd_qi = pert2(f1, f2, in.tnd_qi); in.tnd_ql = pert2(f1, f2, in.tnd_ql); in.tnd_t = pert2(f1, f2, in.tnd_t);
+    in.supsat = ignore_supsat ? axpy(f2, R(0), in.supsat) : pert2(f1, f2, in.supsat);
+    LevelOut<R> o;
+    Traj<R> tr;
+    Trans<R, 0> x;
+    level_fwd<R, C, false>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, false, c, o, tr, x);
+    acc[T_TT][t] += double(o.tnd_t) - double(ref[T_TT]);
+    acc[T_TQ][t] += double(o.tnd_q) - double(ref[T_TQ]);
+    acc[T_TQL][t] += double(o.tnd_ql) - double(ref[T_TQL]);
+    acc[T_TQI][t] += double(o.tnd_qi) - double(ref[T_TQI]);
+    acc[T_CLC][t] += double(o.clc) - double(ref[T_CLC]);
+    acc[T_COVPTOT][t] += double(o.covptot) - double(ref[T_COVPTOT]);
+    acc[T_FPLSL][t] += double(c.rfl) - double(ref[T_FPLSL]);
+    acc[T_FPLSN][t] += double(c.sfl) - double(ref[T_FPLSN]);
+    acc[T_FHPSL][t] += double(-c.rfl * p.RLVTT) - double(ref[T_FHPSL]);
+    acc[T_FHPSN][t] += double(-c.sfl * p.RLSTT) - double(ref[T_FHPSN]);
+    aph0 = in.aph1;
+  }
+  if (!valid) {
+#pragma unroll
+    for (int n = 0; n < T_N; ++n) acc[n][t] = 0.0;  // shadow threads of a ragged last CTA contribute nothing
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // TL: streams [0, 16) = trajectory inputs, [16, 32) = perturbation inputs
 // ---------------------------------------------------------------------------------------
 template <class R>

@@ -185,6 +185,35 @@ nlp_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__
   cs2::dev_column_nl_pert<R, C, kColumnBlock>(p, tab, f, g, fac, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
+__device__ __forceinline__ double warp_sum(double v);
+
+// One Taylor-test factor in one sweep: NL of x + f2 * (f1 * x) and SUM(F_p - F_nl) per output field (cs2_taylor_nl_sums).
+// Per-CTA partial sums go to `partial[field][blockIdx.x]`; taylor_final_kernel adds them up in a fixed order.
+template <class R, class C>
+__global__ void __launch_bounds__(kColumnBlock, 7)
+taylor_nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+                 const __grid_constant__ cs2::NLFields<R> f, R f1, R f2, int ignore_supsat,
+                 const __grid_constant__ cs2::Streams<R, cs2::I_NL + cs2::T_N> in_s, int64_t ncol, int64_t S, int nlev,
+                 double2* __restrict__ partial) {
+  __shared__ cs2::Ring<R, cs2::I_NL + cs2::T_N, kColumnBlock> ring;
+  __shared__ double acc[cs2::T_N][kColumnBlock];
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_nl_taylor<R, C, kColumnBlock>(p, tab, f, f1, f2, ignore_supsat != 0, in_s, ring, acc, uint32_t(S), nlev,
+                                                uint32_t(i), valid);
+  __syncthreads();
+  // fixed-order reduction over the CTA's columns: warp w sums field w, w + 2, ... (kColumnBlock = 64: two warps)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int n = w; n < cs2::T_N; n += kColumnBlock / 32) {
+    double v = 0.0;
+    for (int c0 = lane; c0 < kColumnBlock; c0 += 32) v += acc[n][c0];
+    v = warp_sum(v);
+    if (lane == 0) partial[int64_t(n) * gridDim.x + blockIdx.x] = make_double2(v, 0.0);
+  }
+}
+
 // register caps of the two register-hungry kernels (measured on B200, profiles/README.md): spilling costs far
 // more than the occupancy it buys, the caps below are the largest spill-free values that changed the
 // compiler's allocation for the better
@@ -273,12 +302,16 @@ taylor_partial_kernel(const __grid_constant__ RedPtrs f, int64_t ncol, int64_t S
   const R* b = static_cast<const R*>(f.b[fld]);
   const R* c = static_cast<const R*>(f.c[fld]);
   double s0 = 0.0, s1 = 0.0;
-  const int64_t n = ncol * nlevp1;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t k = e / ncol, i = e - k * ncol;
-    const int64_t off = k * S + i;
-    if (a) s0 += double(a[off]) - (b ? double(b[off]) : 0.0);
-    if (c) s1 += double(c[off]);
+  // blocks stride over (level, 256-column chunk) tiles: no per-element integer division
+  const int64_t chunks = (ncol + blockDim.x - 1) / blockDim.x;
+  const int64_t tiles = chunks * nlevp1;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t k = tile / chunks, i = (tile - k * chunks) * blockDim.x + threadIdx.x;
+    if (i < ncol) {
+      const int64_t off = k * S + i;
+      if (a) s0 += double(a[off]) - (b ? double(b[off]) : 0.0);
+      if (c) s1 += double(c[off]);
+    }
   }
   __shared__ double sh0[8], sh1[8];
   s0 = warp_sum(s0);
@@ -508,6 +541,29 @@ int launch_tl_inc(const cs2_dims* d, const cs2_params* P, double dt, const void*
     tl_inc_kernel<R, false><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor),
                                                          ignore_supsat);
   return check_cuda(cudaGetLastError(), "cloudsc2_tl_increment launch");
+}
+
+template <class R>
+int launch_taylor_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
+                     double factor1, int32_t ignore_supsat, double factor2, double* sums, double2* partial,
+                     cudaStream_t st) {
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
+  const auto ns = cs2::taylor_streams<R>(nf, d->ncol_stride);
+  const unsigned grid = (unsigned)((d->ncol + kColumnBlock - 1) / kColumnBlock);
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  const bool tetens = P->LPHYLIN || P->LDRAIN1D;
+#define CS2_LAUNCH_TNL(E, T)                                                                                              \
+  taylor_nl_kernel<R, cs2::Cfg<E, T>><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, R(factor1), R(factor2), ignore_supsat, ns, \
+                                                                     d->ncol, d->ncol_stride, d->nlev, partial)
+  if (evap && tetens) CS2_LAUNCH_TNL(true, true);
+  else if (evap) CS2_LAUNCH_TNL(true, false);
+  else if (tetens) CS2_LAUNCH_TNL(false, true);
+  else CS2_LAUNCH_TNL(false, false);
+#undef CS2_LAUNCH_TNL
+  if (int rc = check_cuda(cudaGetLastError(), "taylor_nl launch")) return rc;
+  taylor_final_kernel<<<cs2::T_N, 32, 0, st>>>(partial, (int)grid, sums);
+  return check_cuda(cudaGetLastError(), "taylor final launch");
 }
 
 int check_ad_flags(const cs2_params* P, const char* what) {
@@ -770,6 +826,27 @@ int cs2_taylor_sums(const cs2_dims* dims, int32_t nfields, const void* const* a_
   if (int rc = check_cuda(cudaGetLastError(), "taylor partial launch")) return rc;
   taylor_final_kernel<<<nfields, 32, 0, as_stream(stream)>>>(partial, nb, sums_dev);
   return check_cuda(cudaGetLastError(), "taylor final launch");
+}
+
+size_t cs2_taylor_nl_scratch_bytes(const cs2_dims* dims) {
+  if (!dims || dims->ncol < 0) return 0;
+  return size_t((dims->ncol + kColumnBlock - 1) / kColumnBlock) * size_t(cs2::T_N) * sizeof(double2);
+}
+
+int cs2_taylor_nl_sums(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+                       const cs2_nl_fields* f, double factor1, int32_t ignore_supsat, double factor2, double* sums_dev,
+                       void* scratch_dev, size_t scratch_bytes, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev || !sums_dev || !scratch_dev)
+    return fail(CS2_ERR_NULL_POINTER, "taylor_nl_sums: NULL argument");
+  if (int rc = check_nl_fields(f, "taylor_nl_sums fields")) return rc;
+  if (scratch_bytes < cs2_taylor_nl_scratch_bytes(dims)) return fail(CS2_ERR_WORKSPACE, "taylor_nl_sums: scratch too small");
+  if (dims->ncol == 0) return CS2_OK;
+  return dims->dtype == CS2_F64
+             ? launch_taylor_nl<double>(dims, params, dt, level_tables_dev, f, factor1, ignore_supsat, factor2, sums_dev,
+                                        static_cast<double2*>(scratch_dev), as_stream(stream))
+             : launch_taylor_nl<float>(dims, params, dt, level_tables_dev, f, factor1, ignore_supsat, factor2, sums_dev,
+                                       static_cast<double2*>(scratch_dev), as_stream(stream));
 }
 
 int cs2_symmetry_norms(const cs2_dims* dims, int32_t nfields, const void* const* a_dev, const void* const* b_dev,

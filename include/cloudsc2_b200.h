@@ -217,6 +217,22 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt,
            void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * One factor of the Taylor test in ONE sweep (tangent_linear/validation.py:158-176,252-261): the NL of the state
+ * x + factor2 * (factor1 * x) -- StateIncrement(factor1, ignore_supsat) -> PerturbedState(factor2) -> Cloudsc2NL, with the
+ * same roundings as the three stencils -- is evaluated level by level and compared on the fly with the unperturbed NL
+ * outputs: sums_dev[2 * n] += SUM over levels and columns of (F_p - F_nl) for the 10 output fields n in the order
+ * tnd_t, tnd_q, tnd_ql, tnd_qi, clc, fhpsl, fhpsn, fplsl, fplsn, covptot (the order of TaylorTest.get_norm).  `f` holds the
+ * base state x (in_*) and the unperturbed NL outputs F_nl (out_*, READ here); neither the increment, nor the perturbed
+ * state, nor F_p ever reach HBM: 26 field passes per factor instead of 62.  Deterministic (fixed-order partial sums in
+ * `scratch_dev`, cs2_taylor_nl_scratch_bytes(dims) bytes).
+ * ------------------------------------------------------------------------------------- */
+size_t cs2_taylor_nl_scratch_bytes(const cs2_dims* dims);
+int cs2_taylor_nl_sums(const cs2_dims* dims, const cs2_params* params, double dt,
+                       const void* level_tables_dev, const cs2_nl_fields* f, double factor1,
+                       int32_t ignore_supsat, double factor2, double* sums_dev, void* scratch_dev,
+                       size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Validation reductions (device-side replacements of the host NumPy sums of the reference).
  *
  * cs2_taylor_sums -- TaylorTest.get_field_norm (tangent_linear/validation.py:252-261):

@@ -99,7 +99,7 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
     return out
 
 
-def run_taylor(block: str = "base", dtype=np.float64, ncol: int = 100, fused: bool = False):
+def run_taylor(block: str = "base", dtype=np.float64, ncol: int = 100, fused=False):
     cfg, grid, state = make_grid_state(block, dtype, ncol)
     p = iox.ifs_defaults()
     tt = TaylorTest(grid, 0.01, tuple(float(10 ** -(i + 1)) for i in range(10)), 1, True, False, p["yoethf"], p["yomcst"],

@@ -336,6 +336,28 @@ def test_fused_increment_tl_equals_unfused(dtype, ignore_supsat):
                 assert np.abs(b[k].numpy()).max() == 0, k
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ncol", [100, 777])
+def test_taylor_fused_sums_equal_unfused(dtype, ncol):
+    """TaylorTest(fused="sums") -- increment, perturbation, NL and the field sums in one sweep per factor -- gives the same
+    per-field sums (up to summation order) and the same verdict as the reference orchestration; ragged last CTA."""
+    tt_a, norms_a = gh().run_taylor("base", dtype, ncol=ncol, fused=False)
+    tt_b, norms_b = gh().run_taylor("base", dtype, ncol=ncol, fused="sums")
+    sa, sb = tt_a._sums.cpu().numpy(), tt_b._sums.cpu().numpy()
+    # sums of differences F_p - F_nl: compare field by field relative to the largest sum over the factors
+    rtol = 1e-9 if np.dtype(dtype) == np.float64 else 2e-3
+    for fld in range(sa.shape[1]):
+        scale = np.abs(sa[:, fld, :]).max(axis=0)
+        for j in (0, 1):
+            if scale[j] > 0:
+                assert np.abs(sa[:, fld, j] - sb[:, fld, j]).max() <= rtol * scale[j], (fld, j)
+            else:
+                assert np.abs(sb[:, fld, j]).max() == 0, (fld, j)
+    if np.dtype(dtype) == np.float64:
+        np.testing.assert_allclose(norms_b, norms_a, rtol=1e-6)
+        assert tt_a.validate(norms_a, verbose=False) == tt_b.validate(norms_b, verbose=False) == (True, 0)
+
+
 def test_fused_symmetry_test_equals_unfused():
     """SymmetryTest(fused=True): passes like the unfused pipeline, residuals of the same size."""
     st_a, ok_a = gh().run_symmetry("base", np.float64, ncol=257, fused=False)
