@@ -94,9 +94,10 @@ CS2_HD void load_level(const NLFields<R>& f, int64_t S, int64_t i, int k, R aph0
 // NL column (also the forward sweep of AD: `jsel_out` keeps the tropopause candidate)
 // ---------------------------------------------------------------------------------------
 // LIN: keep the linearisation-friendly form of the trajectory (AD forward sweep); false for plain NL
+// cov_out (AD forward sweep with the evaporation branch): the overlap carry entering each level, [nlev][S]
 template <class R, class C, bool LIN = false>
 CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f, int64_t S, int nlev,
-                      int64_t i, bool ad_ref, int32_t* jsel_out) {
+                      int64_t i, bool ad_ref, int32_t* jsel_out, R* cov_out = nullptr) {
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, S, i);
   if (jsel_out) jsel_out[i] = jsel;
   const int ncand = tab.nw + 1;
@@ -118,8 +119,9 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, 0> x;
-    level_fwd<R, C, LIN>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
+    if (cov_out) cov_out[off] = c.covptot;
+    level_fwd<R, C, LIN>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     f.clc[off] = o.clc;
     f.covptot[off] = o.covptot;
     f.o_tnd_q[off] = o.tnd_q;
@@ -222,18 +224,20 @@ CS2_HD void column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
 // trajectory outputs fplsl/fplsn that the forward sweep (column_nl) has just written, the rest
 // of the level trajectory is recomputed from the inputs.
 // ---------------------------------------------------------------------------------------
-template <class R>
+// EVAP: LEVAPLS2 or LDRAIN1D; cov_in = the overlap carry entering each level, written by the forward sweep
+template <class R, bool EVAP = false>
 CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                           const ADSeeds<R>& s, const ADOut<R>& a, const int32_t* jsel_in, int64_t S, int nlev,
-                          int64_t i) {
-  using C = Cfg<false, true>;
+                          int64_t i, const R* cov_in = nullptr) {
+  using C = Cfg<EVAP, true>;
   const bool ad_ref = !p.ad_tl_predicates;
   const int jsel = jsel_in[i];
   const int ncand = tab.nw + 1;
   const R aph_s = f.aph[int64_t(nlev) * S + i];
 
   R a_rfl = R(0), a_sfl = R(0);   // adjoint of the fluxes entering the level below
-  R a_dp_below = R(0);            // a_dp of level k+1 (0 below the surface: tmp_aph_s_i = 0)
+  R a_dp_below = R(0);            // a_dp of level k+1 (0 below the surface)
+  R a_cov = R(0), a_aph_s = R(0); // evaporation branch: adjoint of the overlap carry, adjoint of the surface pressure
   R aph1 = aph_s;
   for (int k = nlev - 1; k >= 0; --k) {
     const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
@@ -245,7 +249,7 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     Carry<R> c;
     c.rfl = (k > 0) ? f.fplsl[off] : R(0);
     c.sfl = (k > 0) ? f.fplsn[off] : R(0);
-    c.covptot = R(0);  // only feeds the (disabled) evaporation branch
+    c.covptot = EVAP ? cov_in[off] : R(0);  // only feeds the evaporation branch
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, 0> x;
@@ -259,14 +263,15 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
     so.tnd_ql = s.tnd_ql[off]; s.tnd_ql[off] = R(0);
     so.tnd_qi = s.tnd_qi[off]; s.tnd_qi[off] = R(0);
     so.clc = s.clc[off];       s.clc[off] = R(0);
-    so.covptot = R(0);         s.covptot[off] = R(0);
+    so.covptot = EVAP ? s.covptot[off] : R(0);
+    s.covptot[off] = R(0);
     R a_rfln = a_rfl + (s.fplsl[offn] - s.fhpsl[offn] * p.RLVTT);
     R a_sfln = a_sfl + (s.fplsn[offn] - s.fhpsn[offn] * p.RLSTT);
     s.fplsl[offn] = R(0); s.fhpsl[offn] = R(0);
     s.fplsn[offn] = R(0); s.fhpsn[offn] = R(0);
 
     LevelIn<R> ad;
-    level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
+    level_ad<R, C>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad, aph_s, &a_cov, &a_aph_s);
     a_rfl = a_rfln;
     a_sfl = a_sfln;
 
@@ -285,6 +290,7 @@ CS2_HD void column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, cons
   }
   a.aph[i] = -a_dp_below;
   a.lu[i] = R(0);
+  if (EVAP) a.aph[int64_t(nlev) * S + i] += a_aph_s;  // adjoint of the surface pressure (AD :974-975)
   s.fplsl[i] = R(0); s.fhpsl[i] = R(0); s.fplsn[i] = R(0); s.fhpsn[i] = R(0);
 }
 

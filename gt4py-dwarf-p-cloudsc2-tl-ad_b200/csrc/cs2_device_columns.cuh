@@ -89,7 +89,8 @@ __device__ __forceinline__ void ring_read_level(const Ring<R, N, BLOCK>& ring, i
 template <class R, class C, int BLOCK, bool CKPT, bool LIN>
 __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const Streams<R, I_NL>& in_s, Ring<R, I_NL, BLOCK>& ring, uint32_t S,
-                                              int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out, R* ck) {
+                                              int nlev, uint32_t i, bool valid, bool ad_ref, int32_t* jsel_out, R* ck,
+                                              R* cov_out = nullptr) {
   ring_issue(ring, in_s, i);  // level 0 is in flight while the tropopause scan runs
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   if (jsel_out && valid) jsel_out[i] = jsel;
@@ -112,6 +113,7 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     LevelIn<R> in;
     ring_read_level(ring, 0, aph0, in);
     if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
+    if (cov_out && valid) cov_out[off] = c.covptot;  // AD forward sweep, evaporation branch: overlap carry entering the level
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, CKPT ? 1 : 0> x;
@@ -403,9 +405,16 @@ enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_F
        B_CK = B_N, B_NCK = B_N + CK_N };
 
 // NS = B_N (recompute) or B_NCK (checkpoint: CK_N more streams with the recorded transcendentals)
-template <class R, int NS>
-inline Streams<R, NS> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int64_t S, int nlev, const R* ck) {
-  Streams<R, NS> o;
+// EVAP (recompute mode only): two more streams after the NS regular ones -- the overlap carry entering each level (written
+// by the forward sweep) and the out_covptot seed
+template <class R, int NS, bool EVAP = false>
+inline Streams<R, NS + (EVAP ? 2 : 0)> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int64_t S, int nlev, const R* ck,
+                                                   const R* cov = nullptr) {
+  Streams<R, NS + (EVAP ? 2 : 0)> o;
+  if constexpr (EVAP) {
+    o.p[NS] = cov;
+    o.p[NS + 1] = s.covptot;
+  }
   if constexpr (NS > B_N) {
     for (int n = 0; n < CK_N; ++n) o.p[B_N + n] = ck + size_t(n) * size_t(nlev) * size_t(S);
   }
@@ -418,12 +427,13 @@ inline Streams<R, NS> ad_streams(const NLFields<R>& f, const ADSeeds<R>& s, int6
   return o;
 }
 
-template <class R, int BLOCK, int NS>
+template <class R, int BLOCK, int NS, bool EVAP = false>
 __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
-                                                  const ADOut<R>& a, const Streams<R, NS>& in_s, Ring<R, NS, BLOCK>& ring,
-                                                  const int32_t* jsel_in, uint32_t S, int nlev, uint32_t i, bool valid) {
+                                                  const ADOut<R>& a, const Streams<R, NS + (EVAP ? 2 : 0)>& in_s,
+                                                  Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, const int32_t* jsel_in,
+                                                  uint32_t S, int nlev, uint32_t i, bool valid) {
   constexpr bool CKPT = NS > B_N;
-  using C = Cfg<false, true>;
+  using C = Cfg<EVAP, true>;
   const bool ad_ref = !p.ad_tl_predicates;
   ring_issue(ring, in_s, uint32_t(nlev - 1) * S + i);
   const int jsel = jsel_in[i];
@@ -432,7 +442,8 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
   const int t = threadIdx.x;
 
   R a_rfl = R(0), a_sfl = R(0);  // adjoint of the fluxes entering the level below
-  R a_dp_below = R(0);           // a_dp of level k+1 (tmp_aph_s_i = 0 without the evaporation branch)
+  R a_dp_below = R(0);           // a_dp of level k+1
+  R a_cov = R(0), a_aph_s = R(0);  // evaporation branch: adjoint of the overlap carry / of the surface pressure
   R aph1 = aph_s;
   for (int k = nlev - 1; k >= 0; --k) {
     const uint32_t off = uint32_t(k) * S + i;
@@ -444,14 +455,14 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     Carry<R> c;
     c.rfl = ring.v[B_FPLSL][t];
     c.sfl = ring.v[B_FPLSN][t];
-    c.covptot = R(0);  // only feeds the (disabled) evaporation branch
+    c.covptot = EVAP ? ring.v[NS][t] : R(0);  // only feeds the evaporation branch
     LevelOut<R> so;
     so.tnd_t = ring.v[B_S_TT][t];
     so.tnd_q = ring.v[B_S_TQ][t];
     so.tnd_ql = ring.v[B_S_TQL][t];
     so.tnd_qi = ring.v[B_S_TQI][t];
     so.clc = ring.v[B_S_CLC][t];
-    so.covptot = R(0);
+    so.covptot = EVAP ? ring.v[NS + 1][t] : R(0);
     // flux seeds at half level k+1 with the enthalpy-flux seeds folded in (AD :479-484,500-501)
     R a_rfln = a_rfl + (ring.v[B_S_FPLSL][t] - ring.v[B_S_FHPSL][t] * p.RLVTT);
     R a_sfln = a_sfl + (ring.v[B_S_FPLSN][t] - ring.v[B_S_FHPSN][t] * p.RLSTT);
@@ -467,7 +478,7 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     Traj<R> tr;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     LevelIn<R> ad;
-    level_ad<R>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad);
+    level_ad<R, C>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad, aph_s, &a_cov, &a_aph_s);
     a_rfl = a_rfln;
     a_sfl = a_sfln;
 
@@ -490,6 +501,7 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
   if (valid) {
     a.aph[i] = -a_dp_below;
     a.lu[i] = R(0);
+    if (EVAP) a.aph[uint32_t(nlev) * S + i] += a_aph_s;  // adjoint of the surface pressure (AD :974-975); own earlier store
   }
 }
 

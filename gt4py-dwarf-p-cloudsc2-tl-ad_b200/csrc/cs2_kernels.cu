@@ -133,14 +133,14 @@ template <class R, class C, bool CKPT, bool LIN>
 __global__ void __launch_bounds__(kColumnBlock, 7)
 nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
-          int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out, R* ck) {
+          int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out, R* ck, R* cov_out) {
   __shared__ cs2::Ring<R, cs2::I_NL, kColumnBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;  // out-of-range threads shadow the last column and store nothing
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
   cs2::dev_column_nl<R, C, kColumnBlock, CKPT, LIN>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0,
-                                               jsel_out, ck);
+                                               jsel_out, ck, cov_out);
 }
 
 #ifndef CS2_BULK_BLOCK
@@ -255,18 +255,18 @@ tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
                                           ignore_supsat != 0);
 }
 
-template <class R, int NS>
-__global__ void __maxnreg__(CS2_AD_MAXNREG)
+template <class R, int NS, bool EVAP>
+__global__ void __maxnreg__(EVAP ? 255 : CS2_AD_MAXNREG)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
-              const __grid_constant__ cs2::Streams<R, NS> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
-              int64_t S, int nlev) {
-  __shared__ cs2::Ring<R, NS, kWideBlock> ring;
+              const __grid_constant__ cs2::Streams<R, NS + (EVAP ? 2 : 0)> in_s, const int32_t* __restrict__ jsel,
+              int64_t ncol, int64_t S, int nlev) {
+  __shared__ cs2::Ring<R, NS + (EVAP ? 2 : 0), kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_ad_bwd<R, kWideBlock, NS>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
+  cs2::dev_column_ad_bwd<R, kWideBlock, NS, EVAP>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
 }
 
 // ---- FP64 pipe micro-benchmark (the roofline's second axis: MEASURED_PEAKS.json has no FP64 entry) -----------
@@ -452,7 +452,7 @@ int launch_state(const cs2_dims* d, double f, int mode, int ignore_supsat, const
 
 template <class R>
 int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
-              bool ad_ref, int32_t* jsel_out, R* ck, cudaStream_t st) {
+              bool ad_ref, int32_t* jsel_out, R* ck, cudaStream_t st, R* cov_out = nullptr) {
   if (d->ncol == 0) return CS2_OK;
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
@@ -462,7 +462,7 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   const bool tetens = P->LPHYLIN || P->LDRAIN1D;
 #define CS2_LAUNCH_NL(E, T)                                                                                         \
   nl_kernel<R, cs2::Cfg<E, T>, false, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
-                                                                            d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr)
+                                                                            d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr, nullptr)
   static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;  // experiment switch (profiles/README.md)
   static const bool use_split = std::getenv("CS2_NL_SPLIT") != nullptr;
   if (use_split && !jsel_out && !evap && d->nlev <= cs2::kSplitMaxLev) {
@@ -479,12 +479,15 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   } else if (use_bulk && !jsel_out && !evap && tetens)
     nl_bulk_kernel<R, cs2::Cfg<false, true>><<<(unsigned)((d->ncol + kBulkBlock - 1) / kBulkBlock), kBulkBlock, 0, st>>>(
         p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
+  else if (cov_out)  // AD forward sweep with the evaporation branch (recompute mode): also stores the overlap carry
+    nl_kernel<R, cs2::Cfg<true, true>, false, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
+                                                                                   d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr, cov_out);
   else if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
     nl_kernel<R, cs2::Cfg<false, true>, true, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
-                                                                                   d->nlev, ad_ref ? 1 : 0, jsel_out, ck);
+                                                                                   d->nlev, ad_ref ? 1 : 0, jsel_out, ck, nullptr);
   else if (jsel_out)  // AD forward sweep, recompute mode
     nl_kernel<R, cs2::Cfg<false, true>, false, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
-                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr);
+                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr, nullptr);
   else if (evap && tetens) CS2_LAUNCH_NL(true, true);
   else if (evap) CS2_LAUNCH_NL(true, false);
   else if (tetens) CS2_LAUNCH_NL(false, true);
@@ -566,15 +569,6 @@ int launch_taylor_nl(const cs2_dims* d, const cs2_params* P, double dt, const vo
   return check_cuda(cudaGetLastError(), "taylor final launch");
 }
 
-int check_ad_flags(const cs2_params* P, const char* what) {
-  if (P->LEVAPLS2 || P->LDRAIN1D)
-    return fail(CS2_ERR_UNSUPPORTED,
-                std::string(what) + ": the precipitation-evaporation branch (LEVAPLS2 / LDRAIN1D) is not implemented "
-                                    "for AD (NL and TL support it); the reference's own TL and AD of that branch are mutually "
-                                    "inconsistent (see DESIGN.md)");
-  return CS2_OK;
-}
-
 cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 }  // namespace
@@ -584,11 +578,13 @@ template <class R>
 int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
               const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, int mode, cudaStream_t st) {
   int32_t* jsel = static_cast<int32_t*>(ws);
-  R* ck = nullptr;
-  if (mode == CS2_AD_CHECKPOINT)
-    ck = reinterpret_cast<R*>(static_cast<char*>(ws) + ((size_t(d->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255)));
+  R* const after_jsel = reinterpret_cast<R*>(static_cast<char*>(ws) + ((size_t(d->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255)));
+  // evaporation branch (LEVAPLS2 / LDRAIN1D, non-default): always the recompute sweep, plus the overlap carry per level
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  R* ck = (!evap && mode == CS2_AD_CHECKPOINT) ? after_jsel : nullptr;
+  R* cov = evap ? after_jsel : nullptr;
   const bool ad_ref = !P->AD_TL_PREDICATES;
-  if (int rc = launch_nl<R>(d, P, dt, tables, traj, ad_ref, jsel, ck, st)) return rc;
+  if (int rc = launch_nl<R>(d, P, dt, tables, traj, ad_ref, jsel, ck, st, cov)) return rc;
   if (d->ncol == 0) return CS2_OK;
   cs2::ADSeeds<R> s;
   s.tnd_t = static_cast<R*>(seeds->in_tnd_t_i); s.tnd_q = static_cast<R*>(seeds->in_tnd_q_i);
@@ -606,12 +602,16 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
   const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*traj);
-  if (ck)
-    ad_bwd_kernel<R, cs2::B_NCK><<<grid, kWideBlock, 0, st>>>(
+  if (evap)
+    ad_bwd_kernel<R, cs2::B_N, true><<<grid, kWideBlock, 0, st>>>(
+        cs2::make_dev_params<R>(*P, dt), tables, nf, a,
+        cs2::ad_streams<R, cs2::B_N, true>(nf, s, d->ncol_stride, d->nlev, nullptr, cov), jsel, d->ncol, d->ncol_stride, d->nlev);
+  else if (ck)
+    ad_bwd_kernel<R, cs2::B_NCK, false><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
         jsel, d->ncol, d->ncol_stride, d->nlev);
   else
-    ad_bwd_kernel<R, cs2::B_N><<<grid, kWideBlock, 0, st>>>(
+    ad_bwd_kernel<R, cs2::B_N, false><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
         jsel, d->ncol, d->ncol_stride, d->nlev);
   if (int rc = check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch")) return rc;
@@ -762,11 +762,13 @@ int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, 
 }
 
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
-  (void)params;
   if (!dims || dims->ncol_stride <= 0) return 0;
   size_t bytes = (size_t(dims->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255);  // tropopause candidate per column
-  if (mode == CS2_AD_CHECKPOINT)  // CK_N transcendental results per (level, column)
-    bytes += size_t(cs2::CK_N) * size_t(dims->nlev) * size_t(dims->ncol_stride) * (dims->dtype == CS2_F32 ? 4 : 8);
+  const size_t plane = size_t(dims->nlev) * size_t(dims->ncol_stride) * (dims->dtype == CS2_F32 ? 4 : 8);
+  if (params && (params->LEVAPLS2 || params->LDRAIN1D))
+    bytes += plane;  // evaporation branch: overlap carry per (level, column); the sweep is always the recompute one
+  else if (mode == CS2_AD_CHECKPOINT)
+    bytes += size_t(cs2::CK_N) * plane;  // CK_N transcendental results per (level, column)
   return (bytes + 255) & ~size_t(255);
 }
 
@@ -781,7 +783,6 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void
   static_assert(sizeof(cs2_ad_outputs) == 16 * sizeof(void*), "cs2_ad_outputs layout");
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(seeds), 10, "cloudsc2_ad seeds")) return rc;
   if (int rc = check_ptrs(reinterpret_cast<const void* const*>(adj), 16, "cloudsc2_ad adjoint outputs")) return rc;
-  if (int rc = check_ad_flags(params, "cloudsc2_ad")) return rc;
   if (mode != CS2_AD_RECOMPUTE && mode != CS2_AD_CHECKPOINT) return fail(CS2_ERR_BAD_DIMS, "cloudsc2_ad: unknown mode");
   if (!workspace_dev || workspace_bytes < cs2_ad_workspace_bytes(dims, params, mode))
     return fail(CS2_ERR_WORKSPACE, "cloudsc2_ad: workspace missing or too small");

@@ -79,6 +79,9 @@ struct Traj {
   bool frz1;
   R rfreeze1;
   R evapr, evaps;
+  // precipitation-evaporation branch (only with Cfg::EVAP; read by level_ad)
+  bool ev, ev_capped, ev_gone;
+  R ev_prtot, ev_rfln, ev_sfln, ev_preclr, ev_qe, ev_beta, ev_b, ev_dtgdp, ev_dpr, covptot_out;
   R t3, qa;
   bool warmc;
   R z3c, z4c, z5c, zalc;
@@ -431,20 +434,34 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
 
   // precipitation evaporation (:288-321) -- dead unless LEVAPLS2 or LDRAIN1D
   tr.evapr = tr.evaps = zero;
+  tr.ev = tr.ev_capped = tr.ev_gone = false;
   o.covptot = zero;
   if (C::EVAP) {
     const R prtot = rfln + sfln;
+    tr.ev_prtot = prtot;
+    tr.ev_rfln = rfln;
+    tr.ev_sfln = sfln;
     if (prtot > p.ZEPS2 && tr.covpclr > p.ZEPS2) {
+      tr.ev = true;
       R preclr = prtot * tr.covpclr / covptot;
+      tr.ev_preclr = preclr;
       const R omc = one - tr.clc_o;
       const R qe = in.qsat - (in.qsat - tr.qlim) * tr.covpclr / (omc * omc);
       const R beta =
           p.RG * p.RPECONS * pow_(sqrt_(in.ap / aph_s) / R(0.00509) * preclr / tr.covpclr, R(0.5777));
       const R b = p.dt * beta * (in.qsat - qe) / (one + p.dt * beta * tr.corqs);
       const R dtgdp = p.dt * p.RG * tr.rdp;
-      const R dpr = min_(tr.covpclr * b / dtgdp, preclr);
+      const R dpr1 = tr.covpclr * b / dtgdp;
+      tr.ev_capped = dpr1 > preclr;
+      const R dpr = min_(dpr1, preclr);
+      tr.ev_qe = qe;
+      tr.ev_beta = beta;
+      tr.ev_b = b;
+      tr.ev_dtgdp = dtgdp;
+      tr.ev_dpr = dpr;
       preclr -= dpr;
-      if (preclr <= zero) covptot = tr.clc_o;
+      tr.ev_gone = preclr <= zero;
+      if (tr.ev_gone) covptot = tr.clc_o;
       o.covptot = covptot;
       tr.evapr = dpr * rfln / prtot;
       rfln -= tr.evapr;
@@ -452,6 +469,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
       sfln -= tr.evaps;
     }
   }
+  tr.covptot_out = covptot;
 
   // first-guess T and q (:328-344)
   R dqdt, dtdt;
@@ -705,9 +723,18 @@ CS2_HD void level_tl(const DevParams<R>& p, const LevelIn<R>& in, const LevelIn<
 //   ad_ref      : backward first freezing test on the post-adjustment temperature (AD :729) and
 //                 the RVTMP2 term on the post-adjustment q (AD :991).
 // ---------------------------------------------------------------------------------------
-template <class R>
+// C::EVAP (LEVAPLS2 or LDRAIN1D): also the reference's adjoint statements of the precipitation-evaporation branch
+// (adjoint/_stencils/cloudsc2.py:635-719,808-817,936-941), restated as they are -- they are NOT the transpose of the TL
+// statements of that branch (TL :577-579 vs AD :668-674; the pressure-thickness adjoint of dtgdp at :664 carries one
+// power of dp; the max-overlap test at :815 cannot fire; a level without evaporation drops the overlap adjoint coming from
+// below, :710-719), so the symmetry test does not hold with these flags in the reference either.
+//   aph_s   : surface pressure of the column (EVAP only)
+//   a_cov   : in = adjoint of the overlap carry LEAVING the level (covptot_i of level k+1), out = entering it
+//   a_aph_s : accumulates the adjoint of aph_s over the levels (added to the aph adjoint of the lowest half level)
+template <class R, class C = Cfg<false, true>>
 CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>& tr, const LevelOut<R>& so,
-                     bool ad_ref, R& a_rfln, R& a_sfln, LevelIn<R>& a) {
+                     bool ad_ref, R& a_rfln, R& a_sfln, LevelIn<R>& a, R aph_s = R(1), R* a_cov = nullptr,
+                     R* a_aph_s = nullptr) {
   const R one = R(1), zero = R(0);
   const R scalm = tr.scalm;
   const R dlv = tr.lsdcp - tr.lvdcp;
@@ -727,6 +754,15 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   R a_ldcp = -so.tnd_t * tr.gdp * in.lude;
   R a_rfreeze = so.tnd_t * dlv * tr.gdp;
   R a_fwat = zero;
+  R a_clc = so.clc;  // adjoint of out_clc
+  R a_evapr = zero, a_evaps = zero;
+  if (C::EVAP) {  // (AD :513-542)
+    a_gdp += -so.tnd_t * (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps) + so.tnd_q * (tr.evapr + tr.evaps);
+    a_evapr = -so.tnd_t * tr.lvdcp * tr.gdp + so.tnd_q * tr.gdp;
+    a_evaps = -so.tnd_t * tr.lsdcp * tr.gdp + so.tnd_q * tr.gdp;
+    a_lvdcp -= so.tnd_t * tr.evapr * tr.gdp;
+    a_lsdcp -= so.tnd_t * tr.evaps * tr.gdp;
+  }
 
   // ---- after the adjustment (AD :565-592)
   R a_dr2, a_dq;
@@ -766,6 +802,76 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_lude_in += (-a_dtdt * tr.ldcp + a_dqdt) * tr.gdp;
   a_ldcp += -a_dtdt * tr.gdp * in.lude;
   a_rfreeze += a_dtdt * dlv * tr.gdp;
+  if (C::EVAP) {  // (AD :605-633)
+    a_gdp += -a_dtdt * (tr.lvdcp * tr.evapr + tr.lsdcp * tr.evaps) + a_dqdt * (tr.evapr + tr.evaps);
+    a_evapr += -a_dtdt * tr.lvdcp * tr.gdp + a_dqdt * tr.gdp;
+    a_evaps += -a_dtdt * tr.lsdcp * tr.gdp + a_dqdt * tr.gdp;
+    a_lvdcp -= a_dtdt * tr.evapr * tr.gdp;
+    a_lsdcp -= a_dtdt * tr.evaps * tr.gdp;
+  }
+
+  // ---- precipitation evaporation (AD :635-719)
+  R a_corqs = zero, a_covpclr = zero, a_qlim = zero, a_qs_ev = zero, a_cov_lvl = zero;
+  if (C::EVAP) {
+    R a_prtot = zero;
+    if (tr.ev) {
+      const R prtot = tr.ev_prtot, dpr = tr.ev_dpr, covpclr = tr.covpclr, covptot1 = tr.covptot1;
+      const R beta = tr.ev_beta, b = tr.ev_b, dtgdp = tr.ev_dtgdp, preclr1 = tr.ev_preclr;
+      // ice, then warm proportion
+      const R e_evaps = a_evaps - a_sfln;
+      const R n_sfln = a_sfln + dpr * e_evaps / prtot;
+      R a_dpr = tr.ev_sfln * e_evaps / prtot;
+      a_prtot = -dpr * tr.ev_sfln * e_evaps / (prtot * prtot);
+      const R e_evapr = a_evapr - a_rfln;
+      const R n_rfln = a_rfln + dpr * e_evapr / prtot;
+      a_dpr += tr.ev_rfln * e_evapr / prtot;
+      a_prtot -= dpr * tr.ev_rfln * e_evapr / (prtot * prtot);
+      // overlap leaving the level: carry from below + the out_covptot seed
+      R a_cv = *a_cov + so.covptot;
+      if (tr.ev_gone) {
+        a_clc += a_cv;
+        a_cv = zero;
+      }
+      R a_preclr = zero;
+      if (tr.ev_capped) {
+        a_preclr = a_dpr;
+        a_dpr = zero;
+      }
+      const R a_b = covpclr * a_dpr / dtgdp;
+      a_covpclr = b * a_dpr / dtgdp;
+      const R a_dtgdp = -covpclr * b * a_dpr / (dtgdp * dtgdp);
+      // implicit solution
+      const R tmp1 = one + p.dt * beta * tr.corqs;
+      const R dqs = in.qsat - tr.ev_qe;
+      const R a_beta = p.dt * dqs * a_b / tmp1 - p.dt * p.dt * beta * dqs * tr.corqs * a_b / (tmp1 * tmp1);
+      a_qs_ev = p.dt * beta * a_b / tmp1;
+      const R a_qe = -p.dt * beta * a_b / tmp1;
+      a_corqs = -(p.dt * p.dt) * beta * dqs * beta * a_b / (tmp1 * tmp1);
+      // humidity in the moistest covpclr region
+      const R sq = sqrt_(in.ap / aph_s);
+      const R xx = R(0.5777) * (p.RG * p.RPECONS / R(0.00509)) * pow_(R(0.00509) * covpclr / (preclr1 * sq), R(0.4223));
+      a_preclr += xx * sq * a_beta / covpclr;
+      const R a_ap_ev = R(0.5) * xx * preclr1 * a_beta / (covpclr * sqrt_(in.ap * aph_s));
+      *a_aph_s -= R(0.5) * xx * preclr1 * sq * a_beta / (covpclr * aph_s);
+      const R omc = one - tr.clc_o;
+      const R romc2 = one / (omc * omc);
+      a_covpclr += -(xx * preclr1 * sq * a_beta / (covpclr * covpclr)) - (in.qsat - tr.qlim) * a_qe * romc2 +
+                   prtot * a_preclr / covptot1;
+      a_qs_ev += a_qe - covpclr * a_qe * romc2;
+      a_qlim = covpclr * a_qe * romc2;
+      a_clc -= R(2) * (in.qsat - tr.qlim) * covpclr * a_qe / (omc * omc * omc);
+      a_prtot += covpclr * a_preclr / covptot1;
+      a_cv -= prtot * covpclr * a_preclr / (covptot1 * covptot1);
+      a_rfln = n_rfln;
+      a_sfln = n_sfln;
+      a_cov_lvl = a_cv;
+      // pressure thickness through dtgdp (AD :664: one power of dp) and the layer pressure through beta
+      a_dp -= p.dt * p.RG * a_dtgdp * tr.rdp;
+      a_ap += a_ap_ev;
+    }
+    a_rfln += a_prtot;
+    a_sfln += a_prtot;
+  }
 
   // ---- new precipitation (AD :721-736)
   const bool frz_b = ad_ref ? (tr.tpost < p.RTT) : tr.frz1;
@@ -780,7 +886,6 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_dp += p.cons2 * (tr.prr + tr.prs) * a_dr1;
 
   // ---- autoconversion (AD :738-782)
-  R a_clc = so.clc;  // adjoint of out_clc
   R a_qlwc1, a_qiwc1;
   if (tr.cloudy) {
     const R a_qinew = a_qiwc - a_prs;
@@ -829,6 +934,18 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_rfln = a_rfl;
   a_sfln = a_sfl;
 
+  // ---- maximum overlap (AD :808-817)
+  if (C::EVAP) {
+    if (tr.covpclr1 < zero) a_covpclr = zero;
+    R a_cv = a_cov_lvl + a_covpclr;
+    a_clc -= a_covpclr;
+    if (tr.clc_o > tr.covptot_out) {  // sic (AD :815): covptot_out >= clc_o always, this never fires
+      a_clc += a_cv;
+      a_cv = zero;
+    }
+    *a_cov = a_cv;
+  }
+
   // ---- condensation rates, liquid / ice split (AD :819-825)
   a_qlwc1 += a_condl * p.rdt;
   a_ql0 -= a_condl * p.rdt;
@@ -856,6 +973,7 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_lsdcp += (one - tr.fwat) * a_ldcp;
   a_rho -= a_rodqsdp * in.qsat * tr.fac2;
   R a_qs = -a_rodqsdp * tr.rho * tr.fac2;
+  if (C::EVAP) a_qs += a_qs_ev;
   const R rq2 = a_rodqsdp * tr.rho * in.qsat * tr.fac2 * tr.fac2;
   a_ap += rq2 + a_rho * tr.fac1;
   R a_foeew = -p.RETV * rq2;
@@ -902,8 +1020,12 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   a_qsat += a_qcrit * tr.crh2;
   a_qs += a_qsat * tr.supsat;
   if (tr.ice) a_t0 -= R(0.003) * a_qsat * in.qsat;
+  if (C::EVAP) {  // qlim = min(q, qsat) (AD :936-938)
+    if (tr.q0 > in.qsat) a_qs += a_qlim; else a_q0 += a_qlim;
+  }
 
   // ---- dqs/dT correction factor (AD :940-967)
+  if (C::EVAP) a_dqsdtemp += p.cons3 * a_corqs;
   a_qs += tr.fac * tr.cor * a_dqsdtemp;
   const R a_cor = tr.fac * in.qsat * a_dqsdtemp;
   const R a_fac = tr.cor * in.qsat * a_dqsdtemp;

@@ -46,7 +46,7 @@ enum {
   CS2_ERR_BAD_DIMS = -1,     /* ncol/nlev/stride/dtype out of range                     */
   CS2_ERR_NULL_POINTER = -2, /* a required pointer is NULL                              */
   CS2_ERR_MISALIGNED = -3,   /* a field pointer is not 16-byte aligned or stride % 32   */
-  CS2_ERR_UNSUPPORTED = -4,  /* flag combination not implemented (message says which)   */
+  CS2_ERR_UNSUPPORTED = -4,  /* reserved: every flag combination is implemented             */
   CS2_ERR_CUDA = -5,         /* CUDA runtime error (message carries cudaGetErrorString) */
   CS2_ERR_WORKSPACE = -6     /* workspace / table buffer too small                      */
 };
@@ -196,6 +196,8 @@ int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt,
  *       (exp / 1+tanh values, 72 B/point in fp64) to the workspace and the backward sweep replays them
  *       instead of re-evaluating them; the cheap algebra is recomputed in both modes.
  *       Both give the same result up to FMA contraction; measured on B200: DESIGN.md section 3.
+ *       With LEVAPLS2 / LDRAIN1D (precipitation-evaporation branch) the sweep is always the recompute one and the
+ *       workspace holds one more plane: the overlap carry entering each level (cs2_ad_workspace_bytes accounts for it).
  * ------------------------------------------------------------------------------------- */
 enum { CS2_AD_RECOMPUTE = 0, CS2_AD_CHECKPOINT = 1 };
 

@@ -59,7 +59,7 @@ void run_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* table
 
 template <class R>
 void run_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
-            const cs2_ad_seeds* sd, const cs2_ad_outputs* ao, int32_t* jsel) {
+            const cs2_ad_seeds* sd, const cs2_ad_outputs* ao, int32_t* jsel, void* cov_ws) {
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
@@ -75,10 +75,17 @@ void run_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* table
   a.tnd_t = (R*)ao->out_tnd_cml_t_i; a.tnd_q = (R*)ao->out_tnd_cml_q_i; a.tnd_ql = (R*)ao->out_tnd_cml_ql_i;
   a.tnd_qi = (R*)ao->out_tnd_cml_qi_i;
   const bool ad_ref = !P->AD_TL_PREDICATES;
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  R* cov = static_cast<R*>(cov_ws);  // [nlev][ncol_stride], evaporation branch only
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < d->ncol; ++i) {
-    cs2::column_nl<R, cs2::Cfg<false, true>, true>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, jsel);
-    cs2::column_ad_bwd<R>(p, tab, nf, s, a, jsel, d->ncol_stride, d->nlev, i);
+    if (evap) {
+      cs2::column_nl<R, cs2::Cfg<true, true>, true>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, jsel, cov);
+      cs2::column_ad_bwd<R, true>(p, tab, nf, s, a, jsel, d->ncol_stride, d->nlev, i, cov);
+    } else {
+      cs2::column_nl<R, cs2::Cfg<false, true>, true>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, jsel);
+      cs2::column_ad_bwd<R, false>(p, tab, nf, s, a, jsel, d->ncol_stride, d->nlev, i);
+    }
   }
 }
 
@@ -117,9 +124,12 @@ int twin_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* table
   if (d->dtype == CS2_F64) run_tl<double>(d, P, dt, tables, f, g); else run_tl<float>(d, P, dt, tables, f, g);
   return 0;
 }
+// cov_ws: (nlev * ncol_stride) elements of scratch, only read/written with LEVAPLS2 / LDRAIN1D (may be NULL otherwise)
 int twin_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,
-            const cs2_ad_seeds* s, const cs2_ad_outputs* a, int32_t* jsel) {
-  if (d->dtype == CS2_F64) run_ad<double>(d, P, dt, tables, f, s, a, jsel); else run_ad<float>(d, P, dt, tables, f, s, a, jsel);
+            const cs2_ad_seeds* s, const cs2_ad_outputs* a, int32_t* jsel, void* cov_ws) {
+  if ((P->LEVAPLS2 || P->LDRAIN1D) && !cov_ws) return 1;
+  if (d->dtype == CS2_F64) run_ad<double>(d, P, dt, tables, f, s, a, jsel, cov_ws);
+  else run_ad<float>(d, P, dt, tables, f, s, a, jsel, cov_ws);
   return 0;
 }
 }

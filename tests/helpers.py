@@ -339,10 +339,12 @@ def twin_ad(s, dt, P, predicates="tl"):
     tab = level_tables(P, s["f_eta"], nlev, h.dtype)
     params, dims = _lib.make_params(dict(P, AD_TL_PREDICATES=(predicates == "tl"))), h.dims()
     jsel = np.zeros(h.stride, dtype=np.int32)
-    twin().twin_ad(
+    cov = np.zeros((nlev, h.stride), dtype=h.dtype)  # overlap carry per level (evaporation branch only)
+    rc = twin().twin_ad(
         C.byref(dims), C.byref(params), C.c_double(dt), C.c_void_p(tab.ctypes.data), C.byref(f), C.byref(seeds),
-        C.byref(outs), C.c_void_p(jsel.ctypes.data),
+        C.byref(outs), C.c_void_p(jsel.ctypes.data), C.c_void_p(cov.ctypes.data),
     )
+    assert rc == 0
     tends, diags = _collect_nl(h)
     tends.update({key: h.get(arg) for arg, key in _AD_OUT_T.items()})
     diags.update({key: h.get(arg) for arg, key in _AD_OUT_D.items()})

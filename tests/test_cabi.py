@@ -65,14 +65,14 @@ def test_argument_validation_without_gpu():
     evap = _lib.make_params(H.externals(LEVAPLS2=True))
     for name, _ in _lib.NLFields._fields_:
         setattr(f, name, p)
-    seeds, outs = _lib.ADSeeds(), _lib.ADOutputs()
-    for st in (seeds, outs):
-        for name, _ in st._fields_:
-            setattr(st, name, p)
-    rc = lib.cs2_ad(C.byref(ok), C.byref(evap), 3600.0, p, C.byref(f), C.byref(seeds), C.byref(outs), p, 1 << 30,
-                    _lib.CS2_AD_RECOMPUTE, None)
-    assert rc == -4  # CS2_ERR_UNSUPPORTED: the evaporation branch exists for NL and TL, not for AD
-    assert b"evaporation" in lib.cs2_last_error()
+    # every flag combination is implemented (NL, TL and AD incl. the evaporation branch): the workspace of AD grows by one
+    # plane with LEVAPLS2 / LDRAIN1D (overlap carry per level) and the checkpoint planes are not used then
+    plain = _lib.make_params(H.externals())
+    big = _lib.Dims(64, 64, 137, _lib.CS2_F64)
+    w_rec = lib.cs2_ad_workspace_bytes(C.byref(big), C.byref(plain), _lib.CS2_AD_RECOMPUTE)
+    w_ck = lib.cs2_ad_workspace_bytes(C.byref(big), C.byref(plain), _lib.CS2_AD_CHECKPOINT)
+    w_ev = lib.cs2_ad_workspace_bytes(C.byref(big), C.byref(evap), _lib.CS2_AD_CHECKPOINT)
+    assert w_rec == 256 and w_ck == 256 + 9 * 137 * 64 * 8 and w_ev == 256 + 137 * 64 * 8
     empty = _lib.Dims(0, 32, 4, _lib.CS2_F64)  # zero columns: nothing to launch, no GPU needed
     assert lib.cs2_saturation(C.byref(empty), C.byref(params), p, p, p, None) == 0
 

@@ -83,6 +83,27 @@ def test_twin_tl_evaporation_branch(block, lregcl, flags):
     H.assert_close_except_total_evaporation_knife_edges({**tt, **td}, {**rt, **rd}, 1e-12, max_columns=2, what=f"TL {flags}: ")
 
 
+@pytest.mark.parametrize("flags", [dict(LEVAPLS2=True), dict(LDRAIN1D=True)])
+@pytest.mark.parametrize("predicates", ["tl", "reference"])
+@pytest.mark.parametrize("block", ["base", "cold"])
+def test_twin_ad_evaporation_branch(block, predicates, flags):
+    """AD with the precipitation-evaporation branch against the oracle's literal restatement of
+    adjoint/_stencils/cloudsc2.py:635-719,808-817,936-941, seeded with the TL outputs like the symmetry harness."""
+    P = H.externals(LREGCL=True, **flags)
+    _, _, _, o = H.oracle_symmetry(H.make_state(block), P, predicates=predicates)
+    assert np.count_nonzero(o["diags_tl"]["f_covptot_i"]) > 0 or block == "cold"
+    ad_in = dict(o["state"])
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = o["tends_tl"][f"f_{x}_i"].copy()
+    for k, v in o["diags_tl"].items():
+        ad_in[k] = v.copy()
+    tad, dad, consumed = H.twin_ad(ad_in, H.DT, P, predicates=predicates)
+    H.assert_close_except_total_evaporation_knife_edges({**tad, **dad}, {**o["tends_ad"], **o["diags_ad"]}, 1e-12,
+                                                        max_columns=2, what=f"AD {flags} {predicates}: ")
+    for k, v in consumed.items():
+        assert not v.any(), f"seed {k} not zeroed"
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("block,predicates", [("base", "tl"), ("base", "reference"), ("cold", "tl")])
 def test_twin_ad(block, predicates, dtype):
