@@ -113,7 +113,7 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     LevelIn<R> in;
     ring_read_level(ring, 0, aph0, in);
     if (k + 1 < nlev) ring_issue(ring, in_s, off + S);
-    if (cov_out && valid) cov_out[off] = c.covptot;  // AD forward sweep, evaporation branch: overlap carry entering the level
+    if (C::EVAP && LIN && cov_out && valid) cov_out[off] = c.covptot;  // AD forward sweep with the evaporation branch only
     LevelOut<R> o;
     Traj<R> tr;
     Trans<R, CKPT ? 1 : 0> x;
