@@ -361,6 +361,39 @@ def run_gpu_arm(args):
                                    "frac_hbm": gbs / peak, "step_ms": step32_ms, "step_columns_per_s": ncol / (step32_ms * 1e-3)}
             del state32, t32, g32, d32
             torch.cuda.empty_cache()
+        if world == 1:
+            # BASELINE.json configs 3 and 4: wall time of one Taylor run (10 factors) and one symmetry run on these columns,
+            # with the reference orchestration and with the opt-in fused sweeps (host clock around a synchronised run)
+            from cloudsc2_b200.physics.tangent_linear.validation import TaylorTest
+
+            def wall(fn, reps=5):
+                for _ in range(2):  # the first call allocates the output fields and the workspaces
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / reps * 1e3
+
+            f2s = tuple(float(10 ** -(i + 1)) for i in range(10))
+            runs = {}
+            for label, fused in (("taylor_run_ms", False), ("taylor_run_fused_sums_ms", "sums")):
+                pt = iox.ifs_defaults()
+                tt = TaylorTest(grid, 0.01, f2s, 1, True, False, pt["yoethf"], pt["yomcst"], pt["yrecldp"], pt["yrephli"],
+                                pt["yrncl"], pt["yrphnc"], gt4py_config=cfg, fused=fused)
+                runs[label] = wall(lambda: tt.run(state, dt))
+                runs[label.replace("_ms", "_penalty")] = tt.validate(tt.run(state, dt), verbose=False)[1]
+                del tt
+                torch.cuda.empty_cache()
+            for label, fused in (("symmetry_run_ms", False), ("symmetry_run_fused_ms", True)):
+                ps = iox.ifs_defaults()
+                stt = SymmetryTest(grid, 0.01, 1, True, False, ps["yoethf"], ps["yomcst"], ps["yrecldp"], ps["yrephli"],
+                                   ps["yrncl"], ps["yrphnc"], gt4py_config=cfg, fused=fused)
+                runs[label] = wall(lambda: stt(state, dt, enable_validation=True, verbose=False))
+                del stt
+                torch.cuda.empty_cache()
+            variants["validation_runs"] = runs
 
     # ---- end to end with HOST buffers through the public host pipeline (cloudsc2_b200.pipeline): the batch lives in
     #      pinned host memory as NPROMA-style column blocks; per block one H2D copy of the 15 packed inputs, the
