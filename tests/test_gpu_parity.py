@@ -450,7 +450,7 @@ def test_one_million_columns_nl_tiling_property():
         assert np.abs(ref).max() == 0 and np.abs(first).max() == 0 or H.field_err(first, ref) <= 1e-12, name
 
 
-@pytest.mark.parametrize("nz,dt", [(60, 900.0), (20, 1800.0)])
+@pytest.mark.parametrize("nz,dt", [(60, 900.0), (20, 1800.0), (3, 3600.0), (1, 3600.0)])
 def test_other_level_counts_and_timesteps(nz, dt):
     from cloudsc2_b200 import synthetic
 

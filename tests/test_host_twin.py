@@ -225,3 +225,30 @@ def test_twin_saturation_flag_paths(flags, dtype):
     got = H.twin_saturation(st["f_ap"], st["f_t"], P)
     assert H.field_err(got, ref) <= H.TOL[np.dtype(dtype)]
     assert not got[137].any()  # the padding level is outside the stencil's domain
+
+
+@pytest.mark.parametrize("nz", [1, 2, 3, 7])
+def test_twin_tiny_level_counts(nz):
+    """Degenerate columns (1-7 levels: no tropopause window, the level below the bottom level is the padding level):
+    NL, TL and AD still equal the oracle."""
+    from cloudsc2_b200 import synthetic
+
+    P = H.externals(LREGCL=True)
+    st = {k: np.ascontiguousarray(v) for k, v in synthetic.base_block(nz=nz).items()}
+    _, _, _, ref = H.oracle_symmetry(st, P, predicates="tl")
+    s = ref["state"]
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    ttn, tdg = H.twin_nl(s, H.DT, P)
+    H.assert_fields_close(ttn, tn, 1e-12, "NL: ")
+    H.assert_fields_close(tdg, dg, 1e-12, "NL: ")
+    tt, td = H.twin_tl(s, H.DT, P)
+    H.assert_fields_close(tt, ref["tends_tl"], 1e-12, "TL: ")
+    H.assert_fields_close(td, ref["diags_tl"], 1e-12, "TL: ")
+    ad_in = dict(s)
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = ref["tends_tl"][f"f_{x}_i"].copy()
+    for k, v in ref["diags_tl"].items():
+        ad_in[k] = v.copy()
+    tad, dad, _ = H.twin_ad(ad_in, H.DT, P, predicates="tl")
+    H.assert_fields_close(tad, ref["tends_ad"], 1e-12, "AD: ")
+    H.assert_fields_close(dad, ref["diags_ad"], 1e-12, "AD: ")
