@@ -95,7 +95,7 @@ SIGNATURES = {
     "cs2_tl_increment": (
         C.c_int,
         [C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.POINTER(NLFields), C.c_double,
-         C.c_int32, C.c_void_p],
+         C.c_int32, C.c_void_p, C.c_void_p],
     ),
     "cs2_nl_perturbed": (
         C.c_int,
@@ -112,6 +112,13 @@ SIGNATURES = {
         [
             C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.POINTER(ADSeeds),
             C.POINTER(ADOutputs), C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p,
+        ],
+    ),
+    "cs2_ad_norm2": (
+        C.c_int,
+        [
+            C.POINTER(Dims), C.POINTER(Params), C.c_double, C.c_void_p, C.POINTER(NLFields), C.POINTER(ADSeeds),
+            C.POINTER(ADOutputs), C.c_void_p, C.c_size_t, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
         ],
     ),
     "cs2_taylor_scratch_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),

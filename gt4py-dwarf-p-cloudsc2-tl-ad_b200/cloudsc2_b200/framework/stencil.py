@@ -301,10 +301,14 @@ class Cloudsc2TLIncrementStencil(StencilObject):
     adjoint/validation.py:136-140 run them back to back) -> cs2_tl_increment.  Takes the trajectory inputs `in_*`,
     the factor `f` and both output sets; the `in_*_i` perturbations are formed in the kernel as f * in_*."""
 
-    def __call__(self, *, in_eta, dt, f, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None, **fields):
+    def __call__(self, *, in_eta, dt, f, norm1=None, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None,
+                 **fields):
+        """`norm1`: optional fp64 device tensor [ncol]; receives SUM_k SUM_fields (TL output)^2 per column."""
         ref = fields["in_ap"]
         dims = self._dims(ref, "in_ap")
         self._check_domain(domain, dims.ncol, dims.nlev + 1)
+        if norm1 is not None:
+            assert norm1.dtype == torch.float64 and norm1.numel() >= dims.ncol and norm1.device == ref.device
         traj = _nl_struct(self, fields, dims)
         pert = _lib.NLFields()
         for name in _lib.NL_OUT_NAMES:
@@ -314,6 +318,7 @@ class Cloudsc2TLIncrementStencil(StencilObject):
             _lib.check(
                 self.lib.cs2_tl_increment(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(), C.byref(traj),
                                           C.byref(pert), float(f), int(bool(self.externals.get("IGNORE_SUPSAT", False))),
+                                          norm1.data_ptr() if norm1 is not None and norm1.numel() else None,
                                           self._stream(ref)),
                 "cs2_tl_increment",
             )
@@ -333,7 +338,10 @@ class Cloudsc2ADStencil(StencilObject):
         self.mode = _lib.CS2_AD_CHECKPOINT if mode == "checkpoint" else _lib.CS2_AD_RECOMPUTE
         self._workspace: Optional[torch.Tensor] = None
 
-    def __call__(self, *, in_eta, dt, origin=(0, 0, 0), domain=None, validate_args=False, exec_info=None, **fields):
+    def __call__(self, *, in_eta, dt, norm2=None, increment_factor=None, origin=(0, 0, 0), domain=None, validate_args=False,
+                 exec_info=None, **fields):
+        """`norm2` (+ `increment_factor`; IGNORE_SUPSAT from the externals): optional fp64 device tensor [ncol]; receives
+        SUM_k SUM_fields (factor * input) * (adjoint output) per column from the backward sweep (cs2_ad_norm2)."""
         ref = fields["in_ap"]
         dims = self._dims(ref, "in_ap")
         self._check_domain(domain, dims.ncol, dims.nlev + 1)
@@ -349,6 +357,17 @@ class Cloudsc2ADStencil(StencilObject):
         if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != ref.device:
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
         with self._Timer(self, exec_info, ref.device):
+            if norm2 is not None and dims.ncol > 0:
+                assert norm2.dtype == torch.float64 and norm2.numel() >= dims.ncol and norm2.device == ref.device
+                _lib.check(
+                    self.lib.cs2_ad_norm2(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(), C.byref(f),
+                                          C.byref(seeds), C.byref(outs), self._workspace.data_ptr(), self._workspace.numel(),
+                                          self.mode, float(increment_factor),
+                                          int(bool(self.externals.get("IGNORE_SUPSAT", False))), norm2.data_ptr(),
+                                          self._stream(ref)),
+                    "cs2_ad_norm2",
+                )
+                return
             _lib.check(
                 self.lib.cs2_ad(C.byref(dims), C.byref(self.params), float(dt), tables.data_ptr(), C.byref(f),
                                 C.byref(seeds), C.byref(outs), self._workspace.data_ptr(), self._workspace.numel(),

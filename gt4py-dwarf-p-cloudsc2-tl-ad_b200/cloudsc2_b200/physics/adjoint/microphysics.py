@@ -39,8 +39,13 @@ AD_DIAG_ADJOINTS = ("aph", "ap", "q", "qsat", "t", "ql", "qi", "lude", "lu", "mf
 class Cloudsc2AD(ImplicitTendencyComponent):
     def __init__(self, computational_grid, lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params,
                  yrephli_params, yrncl_params, yrphnc_params, *, enable_checks=True, gt4py_config,
-                 ad_predicates=None, ad_trajectory=None):
+                 ad_predicates=None, ad_trajectory=None, symmetry_increment=None):
+        """`symmetry_increment=(factor, ignore_supsat)` + the attribute `norm2` (fp64 device tensor [nx]): every call also
+        leaves SUM_k SUM_fields (factor * input) * (adjoint output) per column in `norm2` -- the second inner product of
+        the symmetry test (adjoint/validation.py:183-215), from the backward sweep itself (cs2_ad_norm2)."""
         super().__init__(computational_grid, enable_checks=enable_checks, gt4py_config=gt4py_config)
+        self.symmetry_increment = symmetry_increment
+        self.norm2 = None
         nk = self.computational_grid.grids[I, J, K].shape[2]
         self.klevel = gt_zeros(self.computational_grid, (K,), gt4py_config=self.gt4py_config, dtype_name="int")
         self.klevel[:] = self.klevel.new_tensor(np.arange(0, nk + 1))
@@ -54,7 +59,8 @@ class Cloudsc2AD(ImplicitTendencyComponent):
         self.ad_trajectory = ad_trajectory or os.environ.get("CS2_AD_TRAJECTORY", "checkpoint")
         externals = physics_externals(lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params, yrephli_params,
                                       yrncl_params, yrphnc_params, NLEV=nk,
-                                      AD_TL_PREDICATES=(ad_predicates == "tl"), AD_TRAJECTORY=self.ad_trajectory)
+                                      AD_TL_PREDICATES=(ad_predicates == "tl"), AD_TRAJECTORY=self.ad_trajectory,
+                                      IGNORE_SUPSAT=bool(symmetry_increment[1]) if symmetry_increment else False)
         self.cloudsc2 = self.compile_stencil("cloudsc2_ad", externals)
 
     @cached_property
@@ -88,6 +94,8 @@ class Cloudsc2AD(ImplicitTendencyComponent):
             kwargs.update({f"out_tnd_{n}": out_tendencies[f"f_{n}"] for n in NL_TENDENCIES})
             kwargs.update({f"out_{n}_i": out_diagnostics[f"f_{n}_i"] for n in AD_DIAG_ADJOINTS})
             kwargs.update({f"out_tnd_cml_{n}_i": out_tendencies[f"f_cml_{n}_i"] for n in NL_TENDENCIES})
+            if self.norm2 is not None and self.symmetry_increment is not None:
+                kwargs.update(norm2=self.norm2, increment_factor=self.gt4py_config.dtypes.float(self.symmetry_increment[0]))
             self.cloudsc2(
                 **kwargs, in_eta=state["f_eta"],
                 tmp_aph_s=aph_s, tmp_aph_s_i=aph_s_i, tmp_covptotp=covptotp, tmp_klevel=self.klevel,

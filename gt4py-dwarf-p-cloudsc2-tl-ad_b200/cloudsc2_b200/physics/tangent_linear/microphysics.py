@@ -80,6 +80,9 @@ class IncrementedCloudsc2TL(Cloudsc2TL):
         self.f = gt4py_config.dtypes.float(factor)
         externals = dict(self.cloudsc2.externals, IGNORE_SUPSAT=bool(ignore_supsat))
         self.cloudsc2_increment = self.compile_stencil("cloudsc2_tl_increment", externals)
+        # optional fp64 device tensor [nx]: if set, every call also leaves SUM_k SUM_fields (TL output)^2 per column in
+        # it -- the first inner product of the symmetry test (adjoint/validation.py:167-181), from the sweep itself
+        self.norm1 = None
 
     @cached_property
     def input_grid_properties(self):
@@ -94,7 +97,8 @@ class IncrementedCloudsc2TL(Cloudsc2TL):
             kwargs.update({f"out_{n}{sfx}": out_diagnostics[f"f_{n}{sfx}"] for n in NL_DIAGNOSTICS})
             kwargs.update({f"out_tnd_{n}{sfx}": out_tendencies[f"f_{n}{sfx}"] for n in NL_TENDENCIES})
         self.cloudsc2_increment(
-            **kwargs, in_eta=state["f_eta"], f=self.f, dt=self.gt4py_config.dtypes.float(timestep.total_seconds()),
+            **kwargs, in_eta=state["f_eta"], f=self.f, norm1=self.norm1,
+            dt=self.gt4py_config.dtypes.float(timestep.total_seconds()),
             origin=(0, 0, 0), domain=self.computational_grid.grids[I, J, K - 1 / 2].shape,
             validate_args=self.gt4py_config.validate_args, exec_info=self.gt4py_config.exec_info,
         )

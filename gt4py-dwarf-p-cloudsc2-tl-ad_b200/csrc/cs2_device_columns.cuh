@@ -328,12 +328,16 @@ inline Streams<R, 2 * I_NL> tl_streams(const NLFields<R>& f, const NLFields<R>& 
 // INC: fused "state_increment" + "cloudsc2_tl" (cs2_tl_increment): the perturbation of every input is fac * input
 // (common/_stencils/state_increment.py:60-80; supsat_i = 0 with IGNORE_SUPSAT), formed in registers -- only the 16
 // trajectory inputs are streamed.
-template <class R, int BLOCK, bool INC = false, bool EVAP = false>
+// NORM (with INC): also the symmetry test's first inner product, norm1[i] = SUM_k SUM_fields (TL output)^2 of the column
+// (adjoint/validation.py:167-181), accumulated in fp64 from the values as stored.
+template <class R, int BLOCK, bool INC = false, bool EVAP = false, bool NORM = false>
 __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                               const NLFields<R>& g, const Streams<R, (INC ? 1 : 2) * I_NL>& in_s,
                                               Ring<R, (INC ? 1 : 2) * I_NL, BLOCK>& ring, uint32_t S, int nlev, uint32_t i,
-                                              bool valid, R fac = R(0), bool ignore_supsat = false) {
+                                              bool valid, R fac = R(0), bool ignore_supsat = false,
+                                              double* norm1 = nullptr) {
   using C = Cfg<EVAP, true>;
+  double n1 = 0.0;
   ring_issue(ring, in_s, i);
   const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, int64_t(S), int64_t(i));
   const int ncand = tab.nw + 1;
@@ -387,8 +391,16 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
       f.fhpsl[offn] = -c.rfl * p.RLVTT; g.fhpsl[offn] = -ci.rfl * p.RLVTT;
       f.fhpsn[offn] = -c.sfl * p.RLSTT; g.fhpsn[offn] = -ci.sfl * p.RLSTT;
     }
+    if constexpr (NORM) {
+      auto sq = [](R v) { return double(v) * double(v); };
+      n1 += sq(oi.tnd_t) + sq(oi.tnd_q) + sq(oi.tnd_ql) + sq(oi.tnd_qi) + sq(oi.clc) + sq(oi.covptot) + sq(ci.rfl) +
+            sq(ci.sfl) + sq(-ci.rfl * p.RLVTT) + sq(-ci.sfl * p.RLSTT);
+    }
     aph0 = in.aph1;
     aph0_i = d.aph1;
+  }
+  if constexpr (NORM) {
+    if (valid) norm1[i] = n1;
   }
 }
 
@@ -427,12 +439,18 @@ inline Streams<R, NS + (EVAP ? 2 : 0)> ad_streams(const NLFields<R>& f, const AD
   return o;
 }
 
-template <class R, int BLOCK, int NS, bool EVAP = false>
+// NORM: also the symmetry test's second inner product, norm2[i] = SUM_k SUM_fields (fac * input) * (adjoint output) of the
+// column (adjoint/validation.py:183-215; the increments are StateIncrement's: products rounded on their own, supsat_i = 0
+// with ignore_supsat), accumulated in fp64 from the values as stored.
+template <class R, int BLOCK, int NS, bool EVAP = false, bool NORM = false>
 __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
                                                   const ADOut<R>& a, const Streams<R, NS + (EVAP ? 2 : 0)>& in_s,
                                                   Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, const int32_t* jsel_in,
-                                                  uint32_t S, int nlev, uint32_t i, bool valid) {
+                                                  uint32_t S, int nlev, uint32_t i, bool valid, R fac = R(0),
+                                                  bool ignore_supsat = false, double* norm2 = nullptr,
+                                                  R (*keep)[BLOCK] = nullptr) {
   constexpr bool CKPT = NS > B_N;
+  double n2 = 0.0;
   using C = Cfg<EVAP, true>;
   const bool ad_ref = !p.ad_tl_predicates;
   ring_issue(ring, in_s, uint32_t(nlev - 1) * S + i);
@@ -452,6 +470,13 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     ring_read_level(ring, 0, R(0), in);
     in.aph0 = in.aph1;  // stream I_APH1 carries aph[k] in this sweep
     in.aph1 = aph1;
+    if constexpr (NORM) {
+      // the inner product needs every input again after level_ad: park them in shared memory instead of keeping 16 more
+      // doubles live through the level (the backward kernel has no registers to spare)
+      keep[0][t] = in.t; keep[1][t] = in.q; keep[2][t] = in.ql; keep[3][t] = in.qi; keep[4][t] = in.qsat; keep[5][t] = in.ap;
+      keep[6][t] = in.lude; keep[7][t] = in.mfu; keep[8][t] = in.mfd; keep[9][t] = in.tnd_t; keep[10][t] = in.tnd_q;
+      keep[11][t] = in.tnd_ql; keep[12][t] = in.tnd_qi; keep[13][t] = in.aph1; keep[14][t] = in.lu1; keep[15][t] = in.supsat;
+    }
     Carry<R> c;
     c.rfl = ring.v[B_FPLSL][t];
     c.sfl = ring.v[B_FPLSN][t];
@@ -495,6 +520,15 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
       a.aph[offn] = ad.aph1 - a_dp_below;
       a.lu[offn] = ad.lu1;
     }
+    if constexpr (NORM) {
+      asm volatile("" ::: "memory");
+      auto pr = [fac](R x, R adj) { return double(mul_rn(fac, x)) * double(adj); };
+      n2 += pr(keep[0][t], ad.t) + pr(keep[1][t], ad.q) + pr(keep[2][t], ad.ql) + pr(keep[3][t], ad.qi) +
+            pr(keep[4][t], ad.qsat) + pr(keep[5][t], ad.ap) + pr(keep[6][t], ad.lude) + pr(keep[7][t], ad.mfu) +
+            pr(keep[8][t], ad.mfd) + pr(keep[9][t], ad.tnd_t) + pr(keep[10][t], ad.tnd_q) + pr(keep[11][t], ad.tnd_ql) +
+            pr(keep[12][t], ad.tnd_qi) + pr(keep[13][t], R(ad.aph1 - a_dp_below)) + pr(keep[14][t], ad.lu1);
+      if (!ignore_supsat) n2 += pr(keep[15][t], ad.supsat);
+    }
     a_dp_below = ad.aph1;
     aph1 = in.aph0;
   }
@@ -502,6 +536,10 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     a.aph[i] = -a_dp_below;
     a.lu[i] = R(0);
     if (EVAP) a.aph[uint32_t(nlev) * S + i] += a_aph_s;  // adjoint of the surface pressure (AD :974-975); own earlier store
+    if constexpr (NORM) {
+      n2 += double(mul_rn(fac, aph1)) * double(R(-a_dp_below));  // half level 0 (aph1 holds aph[0] after the loop)
+      norm2[i] = n2;
+    }
   }
 }
 

@@ -240,33 +240,35 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
 }
 
 // fused state_increment + TL (cs2_tl_increment)
-template <class R, bool EVAP>
+template <class R, bool EVAP, bool NORM>
 __global__ void __maxnreg__(EVAP ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
 tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
               const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev, R fac,
-              int ignore_supsat) {
+              int ignore_supsat, double* __restrict__ norm1) {
   __shared__ cs2::Ring<R, cs2::I_NL, kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_tl<R, kWideBlock, true, EVAP>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, fac,
-                                          ignore_supsat != 0);
+  cs2::dev_column_tl<R, kWideBlock, true, EVAP, NORM>(p, tab, f, g, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, fac,
+                                                      ignore_supsat != 0, norm1);
 }
 
-template <class R, int NS, bool EVAP>
+template <class R, int NS, bool EVAP, bool NORM = false>
 __global__ void __maxnreg__(EVAP ? 255 : CS2_AD_MAXNREG)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS + (EVAP ? 2 : 0)> in_s, const int32_t* __restrict__ jsel,
-              int64_t ncol, int64_t S, int nlev) {
+              int64_t ncol, int64_t S, int nlev, R fac = R(0), int ignore_supsat = 0, double* __restrict__ norm2 = nullptr) {
   __shared__ cs2::Ring<R, NS + (EVAP ? 2 : 0), kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
   if (!valid) i = ncol - 1;
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
-  cs2::dev_column_ad_bwd<R, kWideBlock, NS, EVAP>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid);
+  __shared__ R keep[NORM ? 16 : 1][kWideBlock];  // inputs of the current level, for the fused inner product
+  cs2::dev_column_ad_bwd<R, kWideBlock, NS, EVAP, NORM>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid, fac,
+                                                        ignore_supsat != 0, norm2, keep);
 }
 
 // ---- FP64 pipe micro-benchmark (the roofline's second axis: MEASURED_PEAKS.json has no FP64 entry) -----------
@@ -532,17 +534,19 @@ int launch_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
 
 template <class R>
 int launch_tl_inc(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
-                  const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat, cudaStream_t st) {
+                  const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat, double* norm1, cudaStream_t st) {
   const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
   const auto f = cs2::make_nl_fields<R>(*traj), g = cs2::make_nl_fields<R>(*pert_out);
   const auto p = cs2::make_dev_params<R>(*P, dt);
   const auto ns = cs2::nl_streams<R>(f, d->ncol_stride);
-  if (P->LEVAPLS2 || P->LDRAIN1D)
-    tl_inc_kernel<R, true><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor),
-                                                        ignore_supsat);
-  else
-    tl_inc_kernel<R, false><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor),
-                                                         ignore_supsat);
+#define CS2_LAUNCH_TLI(E, N) \
+  tl_inc_kernel<R, E, N><<<grid, kWideBlock, 0, st>>>(p, tables, f, g, ns, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat, norm1)
+  const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
+  if (evap && norm1) CS2_LAUNCH_TLI(true, true);
+  else if (evap) CS2_LAUNCH_TLI(true, false);
+  else if (norm1) CS2_LAUNCH_TLI(false, true);
+  else CS2_LAUNCH_TLI(false, false);
+#undef CS2_LAUNCH_TLI
   return check_cuda(cudaGetLastError(), "cloudsc2_tl_increment launch");
 }
 
@@ -576,7 +580,8 @@ cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 namespace {
 template <class R>
 int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
-              const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, int mode, cudaStream_t st) {
+              const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, int mode, cudaStream_t st,
+              double factor = 0.0, int32_t ignore_supsat = 0, double* norm2 = nullptr) {
   int32_t* jsel = static_cast<int32_t*>(ws);
   R* const after_jsel = reinterpret_cast<R*>(static_cast<char*>(ws) + ((size_t(d->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255)));
   // evaporation branch (LEVAPLS2 / LDRAIN1D, non-default): always the recompute sweep, plus the overlap carry per level
@@ -606,6 +611,14 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
     ad_bwd_kernel<R, cs2::B_N, true><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a,
         cs2::ad_streams<R, cs2::B_N, true>(nf, s, d->ncol_stride, d->nlev, nullptr, cov), jsel, d->ncol, d->ncol_stride, d->nlev);
+  else if (ck && norm2)
+    ad_bwd_kernel<R, cs2::B_NCK, false, true><<<grid, kWideBlock, 0, st>>>(
+        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
+        jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat, norm2);
+  else if (norm2)
+    ad_bwd_kernel<R, cs2::B_N, false, true><<<grid, kWideBlock, 0, st>>>(
+        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
+        jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat, norm2);
   else if (ck)
     ad_bwd_kernel<R, cs2::B_NCK, false><<<grid, kWideBlock, 0, st>>>(
         cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
@@ -748,7 +761,7 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt, const void
 
 int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
                      const cs2_nl_fields* traj, const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat,
-                     void* stream) {
+                     double* norm1_dev, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_tl_increment: params or level tables NULL");
   if (int rc = check_nl_fields(traj, "cloudsc2_tl_increment trajectory fields")) return rc;
@@ -757,8 +770,10 @@ int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, 
     return rc;
   if (dims->ncol == 0) return CS2_OK;
   return dims->dtype == CS2_F64
-             ? launch_tl_inc<double>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, as_stream(stream))
-             : launch_tl_inc<float>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, as_stream(stream));
+             ? launch_tl_inc<double>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, norm1_dev,
+                                     as_stream(stream))
+             : launch_tl_inc<float>(dims, params, dt, level_tables_dev, traj, pert_out, factor, ignore_supsat, norm1_dev,
+                                    as_stream(stream));
 }
 
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
@@ -789,6 +804,32 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void
   return dims->dtype == CS2_F64
              ? launch_ad<double>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream))
              : launch_ad<float>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream));
+}
+
+int cs2_ad_norm2(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,
+           const cs2_nl_fields* traj, const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* workspace_dev,
+           size_t workspace_bytes, int32_t mode, double factor, int32_t ignore_supsat, double* norm2_dev,
+                 void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!params || !level_tables_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_ad: params or level tables NULL");
+  if (int rc = check_nl_fields(traj, "cloudsc2_ad trajectory fields")) return rc;
+  if (!seeds || !adj) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_ad: seeds or adjoint outputs NULL");
+  static_assert(sizeof(cs2_ad_seeds) == 10 * sizeof(void*), "cs2_ad_seeds layout");
+  static_assert(sizeof(cs2_ad_outputs) == 16 * sizeof(void*), "cs2_ad_outputs layout");
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(seeds), 10, "cloudsc2_ad seeds")) return rc;
+  if (int rc = check_ptrs(reinterpret_cast<const void* const*>(adj), 16, "cloudsc2_ad adjoint outputs")) return rc;
+  if (!norm2_dev) return fail(CS2_ERR_NULL_POINTER, "cloudsc2_ad_norm2: norm2_dev is NULL");
+  if (params->LEVAPLS2 || params->LDRAIN1D)
+    return fail(CS2_ERR_UNSUPPORTED, "cloudsc2_ad_norm2: the fused inner product is not built for the evaporation branch "
+                                     "(LEVAPLS2 / LDRAIN1D); use cs2_ad + cs2_symmetry_norms");
+  if (mode != CS2_AD_RECOMPUTE && mode != CS2_AD_CHECKPOINT) return fail(CS2_ERR_BAD_DIMS, "cloudsc2_ad: unknown mode");
+  if (!workspace_dev || workspace_bytes < cs2_ad_workspace_bytes(dims, params, mode))
+    return fail(CS2_ERR_WORKSPACE, "cloudsc2_ad: workspace missing or too small");
+  return dims->dtype == CS2_F64
+             ? launch_ad<double>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream), factor,
+                                  ignore_supsat, norm2_dev)
+             : launch_ad<float>(dims, params, dt, level_tables_dev, traj, seeds, adj, workspace_dev, mode, as_stream(stream), factor,
+                                  ignore_supsat, norm2_dev);
 }
 
 static int taylor_blocks(const cs2_dims* dims) {

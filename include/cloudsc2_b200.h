@@ -46,7 +46,7 @@ enum {
   CS2_ERR_BAD_DIMS = -1,     /* ncol/nlev/stride/dtype out of range                     */
   CS2_ERR_NULL_POINTER = -2, /* a required pointer is NULL                              */
   CS2_ERR_MISALIGNED = -3,   /* a field pointer is not 16-byte aligned or stride % 32   */
-  CS2_ERR_UNSUPPORTED = -4,  /* reserved: every flag combination is implemented             */
+  CS2_ERR_UNSUPPORTED = -4,  /* an opt-in fused entry point is not built for these flags   */
   CS2_ERR_CUDA = -5,         /* CUDA runtime error (message carries cudaGetErrorString) */
   CS2_ERR_WORKSPACE = -6     /* workspace / table buffer too small                      */
 };
@@ -177,10 +177,13 @@ int cs2_tl(const cs2_dims* dims, const cs2_params* params, double dt,
  * The perturbations are bit-identical to cs2_state_increment's (products rounded on their own); the results equal
  * cs2_state_increment followed by cs2_tl up to FMA contraction (field-scaled difference ~1e-14, within the 1e-12 parity tolerance), at 36 instead of
  * 84 field passes through HBM.
+ * norm1_dev (may be NULL): if given, norm1_dev[i] = SUM over levels and the 10 perturbation outputs of (output)^2 for
+ * column i in fp64 -- the first inner product of the symmetry test (adjoint/validation.py:167-181), from the sweep itself.
  * ------------------------------------------------------------------------------------- */
 int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt,
                      const void* level_tables_dev, const cs2_nl_fields* traj,
-                     const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat, void* stream);
+                     const cs2_nl_fields* pert_out, double factor, int32_t ignore_supsat,
+                     double* norm1_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * "cloudsc2_ad" stencil -- adjoint/_stencils/cloudsc2.py:24-996, called from
@@ -217,6 +220,15 @@ int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt,
            const void* level_tables_dev, const cs2_nl_fields* traj, const cs2_ad_seeds* seeds,
            const cs2_ad_outputs* adj, void* workspace_dev, size_t workspace_bytes, int32_t mode,
            void* stream);
+
+/* cs2_ad plus the second inner product of the symmetry test (adjoint/validation.py:183-215) from the backward sweep
+ * itself: norm2_dev[i] = SUM over levels and the 16 state fields of (factor * input) * (adjoint output) for column i in
+ * fp64, with StateIncrement's roundings (supsat_i = 0 when ignore_supsat != 0) -- the increments need not exist in memory.
+ * Not built for LEVAPLS2 / LDRAIN1D (CS2_ERR_UNSUPPORTED: use cs2_ad + cs2_symmetry_norms there). */
+int cs2_ad_norm2(const cs2_dims* dims, const cs2_params* params, double dt,
+                 const void* level_tables_dev, const cs2_nl_fields* traj, const cs2_ad_seeds* seeds,
+                 const cs2_ad_outputs* adj, void* workspace_dev, size_t workspace_bytes, int32_t mode,
+                 double factor, int32_t ignore_supsat, double* norm2_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One factor of the Taylor test in ONE sweep (tangent_linear/validation.py:158-176,252-261): the NL of the state

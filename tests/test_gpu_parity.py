@@ -357,6 +357,12 @@ def test_fused_symmetry_test_equals_unfused():
     st_b, ok_b = gh().run_symmetry("base", np.float64, ncol=257, fused=True)
     assert ok_a and ok_b
     assert st_b.norm3_max < max(1e3, 4 * st_a.norm3_max)
+    # the fused run takes both inner products from the TL / AD sweeps themselves (no increment, no reduction kernels)
+    assert st_b.fused_norms and not st_b.state_i
+    n1a, n1b = st_a.norm1.cpu().numpy(), st_b.norm1.cpu().numpy()
+    n2a, n2b = st_a.norm2.cpu().numpy(), st_b.norm2.cpu().numpy()
+    np.testing.assert_allclose(n1b, n1a, rtol=1e-11)
+    np.testing.assert_allclose(n2b, n2a, rtol=1e-9, atol=1e-12 * np.abs(n2a).max())
 
 
 @pytest.mark.parametrize("flags", [dict(levapls2=True), dict(ldrain1d=True)])
