@@ -304,15 +304,27 @@ taylor_partial_kernel(const __grid_constant__ RedPtrs f, int64_t ncol, int64_t S
   const R* b = static_cast<const R*>(f.b[fld]);
   const R* c = static_cast<const R*>(f.c[fld]);
   double s0 = 0.0, s1 = 0.0;
-  // blocks stride over (level, 256-column chunk) tiles: no per-element integer division
-  const int64_t chunks = (ncol + blockDim.x - 1) / blockDim.x;
-  const int64_t tiles = chunks * nlevp1;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t k = tile / chunks, i = (tile - k * chunks) * blockDim.x + threadIdx.x;
-    if (i < ncol) {
-      const int64_t off = k * S + i;
-      if (a) s0 += double(a[off]) - (b ? double(b[off]) : 0.0);
-      if (c) s1 += double(c[off]);
+  // blocks stride over (level, 256-column chunk) tiles, four tiles in flight per thread (32-bit tile arithmetic: the
+  // launcher's dims check bounds ncol_stride * (nlev + 1) below 2^32)
+  const unsigned chunks = unsigned((ncol + blockDim.x - 1) / blockDim.x);
+  const unsigned tiles = chunks * unsigned(nlevp1);
+  for (unsigned tile = blockIdx.x; tile < tiles; tile += 4u * gridDim.x) {
+    double va[4], vb[4], vc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned tt = tile + unsigned(u) * gridDim.x;
+      const unsigned k = tt / chunks;
+      const int64_t i = int64_t(tt - k * chunks) * blockDim.x + threadIdx.x;
+      const bool ok = tt < tiles && i < ncol;
+      const int64_t off = int64_t(k) * S + i;
+      va[u] = (ok && a) ? double(a[off]) : 0.0;
+      vb[u] = (ok && b) ? double(b[off]) : 0.0;
+      vc[u] = (ok && c) ? double(c[off]) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s0 += va[u] - vb[u];
+      s1 += vc[u];
     }
   }
   __shared__ double sh0[8], sh1[8];
