@@ -110,6 +110,20 @@ struct Trans {
     if (MODE == 1) v[idx] = e;
     return e;
   }
+  // N independent exponentials at once (checkpoint slots idx[n]): evaluated in lockstep on the device (exp_batch)
+  template <int N>
+  CS2_HD void exps(const int (&idx)[N], const R (&x)[N], R (&e)[N]) {
+    if (MODE == 2) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) e[n] = v[idx[n]];
+      return;
+    }
+    exp_batch<N>(x, e);
+    if (MODE == 1) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) v[idx[n]] = e[n];
+    }
+  }
   CS2_HD R tp1(R x) {
     if (MODE == 2) return v[CK_TP1];
     const R e = one_plus_tanh<R>(x);
@@ -402,15 +416,26 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
     tr.rclc = rcp(tr.clc_o);
     tr.cldl = tr.qlwc1 * tr.rclc;
     const R xl = tr.cldl * p.rlcrit;
-    tr.ltmp1 = x.exp(CK_LTMP1, -(xl * xl));
-    tr.ltmp2 = x.exp(CK_LTMP2, -(p.ckcodtl * (one - tr.ltmp1)));
-    tr.qlwc = tr.clc_o * tr.cldl * tr.ltmp2;
-    tr.prr = tr.qlwc1 - tr.qlwc;
     tr.cldi = tr.qiwc1 * tr.rclc;
     const R xi = tr.cldi * p.ricrit;
-    tr.itmp11 = x.exp(CK_ITMP11, -(xi * xi));
-    tr.itmp12 = x.exp(CK_ITMP12, R(0.025) * (tr.tmelt - p.RTT));
-    tr.itmp2 = x.exp(CK_ITMP2, -(p.ckcodti * tr.itmp12 * (one - tr.itmp11)));
+    // the five exponentials of the block form two groups of independent ones: evaluated in lockstep
+    {
+      const int i3[3] = {CK_LTMP1, CK_ITMP11, CK_ITMP12};
+      const R a3[3] = {-(xl * xl), -(xi * xi), R(0.025) * (tr.tmelt - p.RTT)};
+      R e3[3];
+      x.template exps<3>(i3, a3, e3);
+      tr.ltmp1 = e3[0];
+      tr.itmp11 = e3[1];
+      tr.itmp12 = e3[2];
+      const int i2[2] = {CK_LTMP2, CK_ITMP2};
+      const R a2[2] = {-(p.ckcodtl * (one - tr.ltmp1)), -(p.ckcodti * tr.itmp12 * (one - tr.itmp11))};
+      R e2[2];
+      x.template exps<2>(i2, a2, e2);
+      tr.ltmp2 = e2[0];
+      tr.itmp2 = e2[1];
+    }
+    tr.qlwc = tr.clc_o * tr.cldl * tr.ltmp2;
+    tr.prr = tr.qlwc1 - tr.qlwc;
     tr.qiwc = tr.clc_o * tr.cldi * tr.itmp2;
     tr.prs = tr.qiwc1 - tr.qiwc;
   } else {
