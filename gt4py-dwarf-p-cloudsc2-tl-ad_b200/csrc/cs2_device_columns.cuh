@@ -448,7 +448,7 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
                                                   Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, const int32_t* jsel_in,
                                                   uint32_t S, int nlev, uint32_t i, bool valid, R fac = R(0),
                                                   bool ignore_supsat = false, double* norm2 = nullptr,
-                                                  R (*keep)[BLOCK] = nullptr) {
+                                                  R (*keep)[BLOCK] = nullptr, const ADSeeds<R>* zero_seeds = nullptr) {
   constexpr bool CKPT = NS > B_N;
   double n2 = 0.0;
   using C = Cfg<EVAP, true>;
@@ -539,6 +539,20 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     if constexpr (NORM) {
       n2 += double(mul_rn(fac, aph1)) * double(R(-a_dp_below));  // half level 0 (aph1 holds aph[0] after the loop)
       norm2[i] = n2;
+    }
+    // The reference consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).  A column's
+    // seeds are read by this thread only and all of them have been read by now, so the thread resets them itself: a
+    // trailing stream of coalesced stores that overlaps the sweeps of the other warps (inside the level loop the same
+    // stores cost 2-5 %, profiles/r1c_ad_bwd.md; as separate memsets after the kernel they cost 0.13 ms at 65 536 columns).
+    if (zero_seeds) {
+      const ADSeeds<R>& z = *zero_seeds;
+      for (int k = 0; k < nlev; ++k) {
+        const uint32_t off = uint32_t(k) * S + i;
+        z.tnd_t[off] = R(0); z.tnd_q[off] = R(0); z.tnd_ql[off] = R(0); z.tnd_qi[off] = R(0); z.clc[off] = R(0);
+        z.covptot[off] = R(0); z.fhpsl[off] = R(0); z.fhpsn[off] = R(0); z.fplsl[off] = R(0); z.fplsn[off] = R(0);
+      }
+      const uint32_t offb = uint32_t(nlev) * S + i;
+      z.fhpsl[offb] = R(0); z.fhpsn[offb] = R(0); z.fplsl[offb] = R(0); z.fplsn[offb] = R(0);
     }
   }
 }

@@ -260,7 +260,8 @@ __global__ void __maxnreg__(EVAP ? 255 : CS2_AD_MAXNREG)
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS + (EVAP ? 2 : 0)> in_s, const int32_t* __restrict__ jsel,
-              int64_t ncol, int64_t S, int nlev, R fac = R(0), int ignore_supsat = 0, double* __restrict__ norm2 = nullptr) {
+              int64_t ncol, int64_t S, int nlev, R fac, int ignore_supsat, double* __restrict__ norm2,
+              const __grid_constant__ cs2::ADSeeds<R> seeds, int zero_seeds) {
   __shared__ cs2::Ring<R, NS + (EVAP ? 2 : 0), kWideBlock> ring;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < ncol;
@@ -268,7 +269,7 @@ ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
   __shared__ R keep[NORM ? 16 : 1][kWideBlock];  // inputs of the current level, for the fused inner product
   cs2::dev_column_ad_bwd<R, kWideBlock, NS, EVAP, NORM>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(i), valid, fac,
-                                                        ignore_supsat != 0, norm2, keep);
+                                                        ignore_supsat != 0, norm2, keep, zero_seeds ? &seeds : nullptr);
 }
 
 // ---- FP64 pipe micro-benchmark (the roofline's second axis: MEASURED_PEAKS.json has no FP64 entry) -----------
@@ -619,27 +620,24 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
   a.tnd_qi = static_cast<R*>(adj->out_tnd_cml_qi_i);
   const unsigned grid = (unsigned)((d->ncol + kWideBlock - 1) / kWideBlock);
   const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*traj);
-  if (evap)
-    ad_bwd_kernel<R, cs2::B_N, true><<<grid, kWideBlock, 0, st>>>(
-        cs2::make_dev_params<R>(*P, dt), tables, nf, a,
-        cs2::ad_streams<R, cs2::B_N, true>(nf, s, d->ncol_stride, d->nlev, nullptr, cov), jsel, d->ncol, d->ncol_stride, d->nlev);
-  else if (ck && norm2)
-    ad_bwd_kernel<R, cs2::B_NCK, false, true><<<grid, kWideBlock, 0, st>>>(
-        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
-        jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat, norm2);
-  else if (norm2)
-    ad_bwd_kernel<R, cs2::B_N, false, true><<<grid, kWideBlock, 0, st>>>(
-        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
-        jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat, norm2);
-  else if (ck)
-    ad_bwd_kernel<R, cs2::B_NCK, false><<<grid, kWideBlock, 0, st>>>(
-        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_NCK>(nf, s, d->ncol_stride, d->nlev, ck),
-        jsel, d->ncol, d->ncol_stride, d->nlev);
-  else
-    ad_bwd_kernel<R, cs2::B_N, false><<<grid, kWideBlock, 0, st>>>(
-        cs2::make_dev_params<R>(*P, dt), tables, nf, a, cs2::ad_streams<R, cs2::B_N>(nf, s, d->ncol_stride, d->nlev, nullptr),
-        jsel, d->ncol, d->ncol_stride, d->nlev);
+  // seeds are reset by the backward kernel itself (each thread after its own column); CS2_AD_SEED_MEMSET=1 restores
+  // the separate cudaMemsetAsync calls (A/B switch for profiles/)
+  static const bool use_memset = std::getenv("CS2_AD_SEED_MEMSET") != nullptr;
+  const int zero_in_kernel = use_memset ? 0 : 1;
+  const auto dp = cs2::make_dev_params<R>(*P, dt);
+#define CS2_LAUNCH_BWD(NS, E, N, CK, COV)                                                                             \
+  ad_bwd_kernel<R, NS, E, N><<<grid, kWideBlock, 0, st>>>(dp, tables, nf, a,                                             \
+                                                          cs2::ad_streams<R, NS, E>(nf, s, d->ncol_stride, d->nlev, CK, COV), \
+                                                          jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat,  \
+                                                          norm2, s, zero_in_kernel)
+  if (evap) CS2_LAUNCH_BWD(cs2::B_N, true, false, nullptr, cov);
+  else if (ck && norm2) CS2_LAUNCH_BWD(cs2::B_NCK, false, true, ck, nullptr);
+  else if (norm2) CS2_LAUNCH_BWD(cs2::B_N, false, true, nullptr, nullptr);
+  else if (ck) CS2_LAUNCH_BWD(cs2::B_NCK, false, false, ck, nullptr);
+  else CS2_LAUNCH_BWD(cs2::B_N, false, false, nullptr, nullptr);
+#undef CS2_LAUNCH_BWD
   if (int rc = check_cuda(cudaGetLastError(), "cloudsc2_ad backward launch")) return rc;
+  if (zero_in_kernel) return CS2_OK;
   // the reference stencil consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984)
   const size_t full = size_t(d->nlev) * size_t(d->ncol_stride) * sizeof(R);
   const size_t half = size_t(d->nlev + 1) * size_t(d->ncol_stride) * sizeof(R);
