@@ -335,14 +335,14 @@ class Cloudsc2ADStencil(StencilObject):
         mode = str(externals.get("AD_TRAJECTORY", "auto"))
         if mode not in ("recompute", "checkpoint", "auto"):
             raise ValueError("AD_TRAJECTORY must be 'recompute', 'checkpoint' or 'auto'")
-        # "auto": checkpoint up to AUTO_RECOMPUTE_COLUMNS columns per call, recompute above (measured on B200 with the
-        # lockstep exponentials: 1.25 vs 1.29 ms at 65 536 columns, a tie at 262 144, 18.3 vs 17.6 ms at 1 048 576 -- where
-        # the checkpoints would also take 10 GB)
+        # "auto": checkpoint up to AUTO_RECOMPUTE_COLUMNS columns per call, recompute above.  Measured on B200 with the
+        # lockstep exponentials and the in-kernel seed reset: recompute 1.19 vs checkpoint 1.21 ms at 65 536 columns,
+        # 16.2 vs 17.9 ms at 1 048 576 (where the checkpoints would also take 10 GB) -> the threshold is 0.
         self._mode_name = mode
         self.mode = _lib.CS2_AD_CHECKPOINT if mode == "checkpoint" else _lib.CS2_AD_RECOMPUTE
         self._workspace: Optional[torch.Tensor] = None
 
-    AUTO_RECOMPUTE_COLUMNS = 300_000
+    AUTO_RECOMPUTE_COLUMNS = 0
 
     def _resolve_mode(self, ncol: int) -> int:
         if self._mode_name == "auto":

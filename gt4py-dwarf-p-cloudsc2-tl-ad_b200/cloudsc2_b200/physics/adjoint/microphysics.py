@@ -55,8 +55,9 @@ class Cloudsc2AD(ImplicitTendencyComponent):
         self.ad_predicates = ad_predicates
         # "checkpoint": the forward sweep stores the 9 transcendental results per point to an HBM workspace (72 B/point in
         # fp64) and the backward sweep replays them; "recompute": the backward sweep recomputes each level's trajectory
-        # from the inputs (no workspace); "auto" (default): checkpoint up to 300 000 columns per call, recompute above
-        # (measured on B200: checkpoint 3 % faster at 65 536 columns, recompute 4 % faster and 10 GB lighter at 1 M).
+        # from the inputs (no workspace); "auto" (default): whichever measured faster on B200 for the call's size -- with
+        # the lockstep exponentials and the in-kernel seed reset that is recompute everywhere (1 % at 65 536 columns,
+        # 10 % and 10 GB at 1 M).
         self.ad_trajectory = ad_trajectory or os.environ.get("CS2_AD_TRAJECTORY", "auto")
         externals = physics_externals(lphylin, ldrain1d, yoethf_params, yomcst_params, yrecldp_params, yrephli_params,
                                       yrncl_params, yrphnc_params, NLEV=nk,

@@ -413,6 +413,9 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
 // slower (profiles/r1c_ad_bwd.md); zeroing in the kernel one level after the copy completed is correct
 // but still 2-5 % slower than the separate memsets (10 more stores per level in a latency-bound loop).
 // ---------------------------------------------------------------------------------------
+#ifndef CS2_AD_ZERO_LAG
+#define CS2_AD_ZERO_LAG 4  // the backward sweep resets the seeds of the level it consumed this many iterations ago
+#endif
 enum { B_FPLSL = I_NL, B_FPLSN, B_S_TT, B_S_TQ, B_S_TQL, B_S_TQI, B_S_CLC, B_S_FPLSL, B_S_FHPSL, B_S_FPLSN, B_S_FHPSN, B_N,
        B_CK = B_N, B_NCK = B_N + CK_N };
 
@@ -498,6 +501,12 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
       for (int n = 0; n < CK_N; ++n) x.v[n] = ring.v[B_N + n][t];
     }
     if (k > 0) ring_issue(ring, in_s, off - S);
+    if (zero_seeds && valid && k + CS2_AD_ZERO_LAG < nlev) {  // seeds of a level consumed CS2_AD_ZERO_LAG iterations ago
+      const ADSeeds<R>& z = *zero_seeds;
+      const uint32_t zo = off + uint32_t(CS2_AD_ZERO_LAG) * S;
+      z.tnd_t[zo] = R(0); z.tnd_q[zo] = R(0); z.tnd_ql[zo] = R(0); z.tnd_qi[zo] = R(0); z.clc[zo] = R(0);
+      z.covptot[zo] = R(0); z.fhpsl[zo + S] = R(0); z.fhpsn[zo + S] = R(0); z.fplsl[zo + S] = R(0); z.fplsn[zo + S] = R(0);
+    }
 
     LevelOut<R> o;
     Traj<R> tr;
@@ -541,18 +550,23 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
       norm2[i] = n2;
     }
     // The reference consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).  A column's
-    // seeds are read by this thread only and all of them have been read by now, so the thread resets them itself: a
-    // trailing stream of coalesced stores that overlaps the sweeps of the other warps (inside the level loop the same
-    // stores cost 2-5 %, profiles/r1c_ad_bwd.md; as separate memsets after the kernel they cost 0.13 ms at 65 536 columns).
+    // seeds are read by this thread only, so the thread resets them itself: inside the level loop the seeds of the level
+    // consumed CS2_AD_ZERO_LAG iterations earlier (plain stores off the dependent chain, spread over the sweep), here the
+    // last few levels.  Measured at 65 536 columns: 1.29 ms with 10 cudaMemsetAsync after the kernel, 1.25 ms with one
+    // trailing burst of stores, 1.19 ms with the lagged in-loop stores (any lag from 1 to 16); zeroing a slot right after
+    // its own load, as the very first version did, serialises in L2 and was 4x slower (profiles/r1c_ad_bwd.md).
     if (zero_seeds) {
       const ADSeeds<R>& z = *zero_seeds;
-      for (int k = 0; k < nlev; ++k) {
+      const int ktail = nlev < CS2_AD_ZERO_LAG ? nlev : CS2_AD_ZERO_LAG;  // the levels the in-loop reset has not reached
+      for (int k = 0; k < ktail; ++k) {
         const uint32_t off = uint32_t(k) * S + i;
         z.tnd_t[off] = R(0); z.tnd_q[off] = R(0); z.tnd_ql[off] = R(0); z.tnd_qi[off] = R(0); z.clc[off] = R(0);
-        z.covptot[off] = R(0); z.fhpsl[off] = R(0); z.fhpsn[off] = R(0); z.fplsl[off] = R(0); z.fplsn[off] = R(0);
+        z.covptot[off] = R(0);
       }
-      const uint32_t offb = uint32_t(nlev) * S + i;
-      z.fhpsl[offb] = R(0); z.fhpsn[offb] = R(0); z.fplsl[offb] = R(0); z.fplsn[offb] = R(0);
+      for (int k = 0; k <= ktail; ++k) {  // half-level seeds: one more level
+        const uint32_t off = uint32_t(k) * S + i;
+        z.fhpsl[off] = R(0); z.fhpsn[off] = R(0); z.fplsl[off] = R(0); z.fplsn[off] = R(0);
+      }
     }
   }
 }
