@@ -1439,12 +1439,12 @@ def cloudsc2_ad(s, dt, P, predicates="reference"):
                 preclr_i = preclr_i + xx * sq * beta_i / covpclr
                 e_oap_add = 0.5 * xx * n.preclr1 * beta_i / (covpclr * np.sqrt(apk * aph_s))
                 e_aph_s_sub = 0.5 * xx * n.preclr1 * sq * beta_i / (covpclr * aph_s)
-                covpclr_i = covpclr_i + (
+                covpclr_i = covpclr_i + ((
                     -(xx * n.preclr1 * sq * beta_i / covpclr**2.0) - (qsk - n.qlim) * qe_i / (1.0 - oclc) ** 2.0
-                ) + prtot * preclr_i / covptot1
+                ) + prtot * preclr_i / covptot1)  # `+=` of the whole right-hand side, :693-696
                 e_oqsat_i = e_oqsat_i + (qe_i - covpclr * qe_i / (1.0 - oclc) ** 2.0)
                 e_qlim_i = covpclr * qe_i / (1.0 - oclc) ** 2.0
-                e_clc_add = e_clc_add - 2.0 * (qsk - n.qlim) * covpclr * qe_i / (1.0 - oclc) ** 3.0
+                e_clc_sub = 2.0 * (qsk - n.qlim) * covpclr * qe_i / (1.0 - oclc) ** 3.0
                 prtot_i = prtot_i + covpclr * preclr_i / covptot1
                 e_covptot_i = e_covptot_i - prtot * covpclr * preclr_i / covptot1**2.0
 
@@ -1452,7 +1452,7 @@ def cloudsc2_ad(s, dt, P, predicates="reference"):
                 evapr_i = W(ev, e_evapr_i, evapr_i)
                 sfln_i = W(ev, e_sfln_i, sfln_i)
                 rfln_i = W(ev, e_rfln_i, rfln_i)
-                in_clc_i[k] = W(ev, in_clc_i[k] + e_clc_add, in_clc_i[k])
+                in_clc_i[k] = W(ev, (in_clc_i[k] + e_clc_add) - e_clc_sub, in_clc_i[k])  # :656 then :700-706
                 corqs_i = W(ev, e_corqs_i, 0.0).astype(dtype)
                 covpclr_i = W(ev, covpclr_i, 0.0).astype(dtype)
                 covptot_i = W(ev, e_covptot_i, 0.0).astype(dtype)

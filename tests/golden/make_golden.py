@@ -7,9 +7,16 @@ container (needs /root/reference for part 1; part 2 only needs the oracle):
    NL outputs `data/reference_{double,single}.h5` (read with cloudsc2_b200.h5lite, stored
    loss-free with np.savez_compressed).  These are DATA published by the reference for
    validation (drivers/run_nonlinear.py:139-147), not source code.
-2. `oracle_<block>_<precision>.npz`: outputs of the NumPy oracle (oracle/cloudsc2_numpy.py)
-   for NL, TL and AD on the seeded synthetic blocks of cloudsc2_b200.synthetic (first 16
-   columns), so that a drift of the oracle itself is caught by tests/test_oracle.py.
+2. `ref_*.npz` (helpers.REF_FIXTURES): outputs of the REFERENCE'S OWN stencil sources
+   (`/root/reference/src/cloudsc2_gt4py/physics/**/_stencils/*.py`, unmodified, executed by
+   oracle/gtscript_exec.py through oracle/ref_run.py) for saturation, NL, state_increment,
+   perturbed_state, TL and AD on the seeded synthetic blocks of cloudsc2_b200.synthetic,
+   fp64 and fp32, default and non-default flags.  These pin the oracle AND the CUDA kernels
+   to outputs of the reference itself: tests/test_ref_exec.py (CPU), tests/test_gpu_parity.py.
+3. `oracle_<block>_<precision>.npz`: outputs of the NumPy oracle (oracle/cloudsc2_numpy.py)
+   for NL, TL and AD on the same blocks (first 16 columns), incl. the AD with the TL's
+   predicates (not a reference behaviour), so that a drift of the oracle itself is caught
+   by tests/test_oracle.py.
 """
 import os
 import sys
@@ -37,6 +44,20 @@ def golden_from_reference():
         print("wrote", f"reference_{precision}.npz", sorted(f.keys()))
 
 
+def reference_fixtures():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H  # noqa: E402
+    from oracle import ref_run  # noqa: E402
+
+    if not ref_run.available():
+        print("skip ref_*.npz: /root/reference/src not present")
+        return
+    for name, (block, dtype, ncol, flags) in H.REF_FIXTURES.items():
+        out = H.pipeline_run_all(ref_run, block, dtype, ncol, **flags)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("wrote", name + ".npz", len(out), "arrays")
+
+
 def oracle_fixtures(ncol=16):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import oracle_run_all  # noqa: E402
@@ -50,5 +71,6 @@ def oracle_fixtures(ncol=16):
 
 if __name__ == "__main__":
     golden_from_reference()
+    reference_fixtures()
     if "--no-oracle" not in sys.argv:
         oracle_fixtures()

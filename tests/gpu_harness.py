@@ -56,7 +56,7 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
     dt = timedelta(seconds=dt_seconds)
     out: Dict[str, Any] = {}
 
-    sat = Saturation(grid, 1, lphylin, p["yoethf"], p["yomcst"], gt4py_config=cfg)
+    sat = Saturation(grid, int(flags.get("kflag", 1)), lphylin, p["yoethf"], p["yomcst"], gt4py_config=cfg)
     state.update(sat(state))
     out["qsat"] = state["f_qsat"].numpy()
     out["eta"] = state["f_eta"].numpy()
@@ -66,7 +66,7 @@ def run_components(block: str = "base", dtype=np.float64, ncol: int = 100, ad_pr
     if flags.get("nl_only"):
         return out
 
-    st = SymmetryTest(grid, 0.01, 1, lphylin, ldrain1d, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"],
+    st = SymmetryTest(grid, 0.01, int(flags.get("kflag", 1)), lphylin, ldrain1d, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrncl"],
                       p["yrphnc"], gt4py_config=cfg, ad_predicates=ad_predicates, ad_trajectory=ad_trajectory,
                       fused=bool(flags.get("fused", False)))
     if "ignore_supsat" in flags:  # the symmetry harness ignores supsat; the Taylor harness does not

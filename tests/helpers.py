@@ -183,6 +183,57 @@ def oracle_run_all(block: str, dtype, ncol: int) -> Dict[str, np.ndarray]:
     return out
 
 
+SEED_KEYS = ("f_tnd_t_i", "f_tnd_q_i", "f_tnd_ql_i", "f_tnd_qi_i", "f_clc_i", "f_covptot_i", "f_fhpsl_i", "f_fhpsn_i",
+             "f_fplsl_i", "f_fplsn_i")  # adjoint/microphysics.py:106-120
+
+
+def pipeline_run_all(impl, block: str, dtype, ncol: int, ad_kwargs=None, **flags) -> Dict[str, np.ndarray]:
+    """saturation -> NL -> state_increment(0.01, ignore_supsat) -> TL -> AD (the symmetry test's chain,
+    adjoint/validation.py:132-153) plus one perturbed_state, on the first `ncol` columns of a synthetic block,
+    through `impl` = oracle.cloudsc2_numpy (the restatement) or oracle.ref_run (the reference's own stencil
+    sources).  Flattened into one dict: the schema of tests/golden/ref_*.npz."""
+    P = externals(**{"LREGCL": True, **flags})
+    st = {k: np.ascontiguousarray(v[:, :ncol]) for k, v in make_state(block, dtype).items()}
+    s = dict(st)
+    s["f_eta"] = onp.eta_levels(s["f_ap"], s["f_aph"])  # common/diagnostics.py:42-45 (a python loop, not a stencil)
+    s["f_qsat"] = impl.saturation(s["f_ap"], s["f_t"], P)
+    out = {"in_f_eta": s["f_eta"], "in_f_qsat": s["f_qsat"]}
+    tn, dg = impl.cloudsc2_nl(s, DT, P)
+    out.update({"nl_t_" + k: v for k, v in tn.items()})
+    out.update({"nl_d_" + k: v for k, v in dg.items()})
+    si = impl.state_increment(s, 0.01, ignore_supsat=True)
+    s.update(si)
+    out.update({"inc_" + k: v for k, v in si.items()})
+    out.update({"pert_" + k: v for k, v in impl.perturbed_state(s, 1e-3).items()})
+    ttl, dtl = impl.cloudsc2_tl(s, DT, P)
+    out.update({"tl_t_" + k: v.copy() for k, v in ttl.items()})
+    out.update({"tl_d_" + k: v.copy() for k, v in dtl.items()})
+    ad_in = dict(s)
+    for x in ("t", "q", "ql", "qi"):
+        ad_in[f"f_tnd_{x}_i"] = ttl[f"f_{x}_i"].copy()
+    for k, v in dtl.items():
+        ad_in[k] = v.copy()
+    tad, dad = impl.cloudsc2_ad(ad_in, DT, P, **(ad_kwargs or {}))
+    out.update({"ad_t_" + k: v for k, v in tad.items()})
+    out.update({"ad_d_" + k: v for k, v in dad.items()})
+    out.update({"ad_seed_" + k: ad_in[k] for k in SEED_KEYS})
+    return out
+
+
+# the fixtures written from the reference's own sources: name -> (block, precision, ncol, externals overrides)
+REF_FIXTURES = {
+    "ref_base_double": ("base", np.float64, 32, {}),
+    "ref_cold_double": ("cold", np.float64, 32, {}),
+    "ref_base_single": ("base", np.float32, 32, {}),
+    "ref_cold_single": ("cold", np.float32, 32, {}),
+    "ref_base_double_noregcl": ("base", np.float64, 16, {"LREGCL": False}),
+    "ref_base_double_tetens": ("base", np.float64, 16, {"LPHYLIN": False}),
+    "ref_base_double_tetens_kflag0": ("base", np.float64, 16, {"LPHYLIN": False, "KFLAG": 0}),
+    "ref_base_double_levapls2": ("base", np.float64, 16, {"LEVAPLS2": True}),
+    "ref_base_double_ldrain1d": ("base", np.float64, 16, {"LDRAIN1D": True}),
+}
+
+
 # ------------------------------------------------------------------------------------------
 # host twin (csrc column code compiled for the CPU; see oracle/host_twin/twin.cpp)
 # ------------------------------------------------------------------------------------------

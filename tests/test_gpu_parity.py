@@ -122,6 +122,51 @@ def test_against_committed_fixtures(block, precision, dtype):
     H.assert_fields_close(out["diags_ad"], {k[8:]: ref[k] for k in ref.files if k.startswith("ad_tl_d_")}, tol_for("ad_tl_d_"))
 
 
+_REF_CASES = [(name,) + spec for name, spec in H.REF_FIXTURES.items()]
+
+
+@pytest.mark.parametrize("name,block,dtype,ncol,flags", _REF_CASES, ids=[c[0] for c in _REF_CASES])
+def test_against_outputs_of_the_reference_source(name, block, dtype, ncol, flags):
+    """tests/golden/ref_*.npz were written by the reference's OWN stencil files executed in place
+    (oracle/gtscript_exec.py, tests/golden/make_golden.py): saturation, NL, state_increment, TL and the literal
+    AD (`ad_predicates="reference"`), default and non-default flags, through the components and the C ABI."""
+    ref = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out = gh().run_components(
+        block=block, dtype=dtype, ncol=ncol, ad_predicates="reference", lregcl=flags.get("LREGCL", True),
+        levapls2=flags.get("LEVAPLS2", False), ldrain1d=flags.get("LDRAIN1D", False), lphylin=flags.get("LPHYLIN", True),
+        kflag=flags.get("KFLAG", 1),
+    )
+    tol = H.TOL[np.dtype(dtype)]
+    evap = bool(flags.get("LEVAPLS2") or flags.get("LDRAIN1D"))
+    ref64 = np.load(os.path.join(GOLDEN, name.replace("single", "double") + ".npz"))
+
+    def group(prefix, src=ref):
+        return {k[len(prefix):]: src[k] for k in src.files if k.startswith(prefix)}
+
+    def tol_for(prefix, base=tol):
+        if dtype == np.float64:
+            return base
+        return H.fp32_field_tolerances(group(prefix), group(prefix, ref64))
+
+    assert np.array_equal(out["eta"], ref["in_f_eta"])
+    assert H.field_err(out["qsat"], ref["in_f_qsat"]) <= tol
+    H.assert_fields_close(out["state_i"], group("inc_"), tol, "state_increment: ")
+    nl = {**out["tends_nl"], **out["diags_nl"]}
+    tl = {**out["tends_tl"], **out["diags_tl"]}
+    ad = {**out["tends_ad"], **out["diags_ad"]}
+    ref_nl, ref_tl, ref_ad = ({**group(p + "_t_"), **group(p + "_d_")} for p in ("nl", "tl", "ad"))
+    if evap:  # total-evaporation knife edges (helpers.assert_close_except_...) and 1e80-sized adjoints
+        H.assert_close_except_total_evaporation_knife_edges(nl, ref_nl, tol, 1, "NL: ")
+        H.assert_close_except_total_evaporation_knife_edges(tl, ref_tl, tol, 1, "TL: ")
+        H.assert_close_except_total_evaporation_knife_edges(ad, ref_ad, 1e-10, 1, "AD: ")
+    else:
+        H.assert_fields_close(nl, ref_nl, {**tol_for("nl_t_"), **tol_for("nl_d_")} if dtype == np.float32 else tol, "NL: ")
+        H.assert_fields_close(tl, ref_tl, {**tol_for("tl_t_"), **tol_for("tl_d_")} if dtype == np.float32 else tol, "TL: ")
+        H.assert_fields_close(ad, ref_ad, {**tol_for("ad_t_"), **tol_for("ad_d_")} if dtype == np.float32 else tol, "AD: ")
+    for k, v in out["seeds_after"].items():
+        assert not v.any(), f"AD did not consume seed {k}"
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_taylor_test_vshape(dtype):
     """TL Taylor test with device-side sums: V-shape with slope 2 (reference scoring, penalty <= 5)."""
