@@ -20,6 +20,8 @@ def core(config, io_config, ad_predicates=None, fused=False):
                       yomcst_params=p["yomcst"], yrecldp_params=p["yrecldp"], yrephli_params=p["yrephli"],
                       yrncl_params=p["yrncl"], yrphnc_params=p["yrphnc"], enable_checks=config.sympl_enable_checks,
                       gt4py_config=cfg, ad_predicates=ad_predicates, fused=fused)
+    print(f"AD branch predicates: {st.cloudsc2_ad.ad_predicates!r} ('reference' = the reference AD stencil literally; "
+          f"'tl' = the TL sweep's predicates, an exact adjoint on any input; --ad-predicates / CS2_AD_PREDICATES)")
     passed = st(state, dt, enable_validation=True)
     cfg.reset_exec_info()
     runtime_l = []

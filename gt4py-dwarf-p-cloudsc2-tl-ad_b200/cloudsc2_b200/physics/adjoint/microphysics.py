@@ -4,12 +4,16 @@ Side effects kept from the reference stencil: the adjoint seeds found in `state`
 (`f_tnd_{t,q,ql,qi}_i`, `f_clc_i`, `f_covptot_i`, `f_f{h,p}ps{l,n}_i`) are consumed, i.e. zeroed
 in place (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).
 
-`ad_predicates`: "tl" (default) evaluates every branch predicate exactly like the TL sweep on the
-same trajectory, which makes the component the exact adjoint of `Cloudsc2TL` on any input;
-"reference" restates the reference literally (second freezing test on the pre-adjustment
-temperature, backward first-freezing test on the post-adjustment temperature), which is identical
-on all-cold inputs such as the reference's `input.h5` and differs only where a level crosses RTT
-during the saturation adjustment ("AD predicates")."""
+`ad_predicates`: "reference" (default: what a drop-in user of the reference gets) restates the
+reference AD stencil literally -- second freezing test on the pre-adjustment temperature
+(adjoint/_stencils/cloudsc2.py:427,577), backward first-freezing test on the post-adjustment
+temperature (:729); parity-tested against the reference's own stencil source
+(tests/golden/ref_*.npz).  "tl" (opt-in, also `CS2_AD_PREDICATES=tl`) evaluates every branch
+predicate exactly like the TL sweep on the same trajectory, which makes the component the exact
+adjoint of `Cloudsc2TL` on ANY input.  The two are identical on all-cold inputs such as the
+reference's `input.h5` and differ only where a level crosses RTT during the saturation adjustment;
+there the literal mode -- in the reference and here alike -- fails the reference's own symmetry
+test (DESIGN.md, "AD predicates")."""
 from __future__ import annotations
 
 import os
@@ -49,7 +53,7 @@ class Cloudsc2AD(ImplicitTendencyComponent):
         nk = self.computational_grid.grids[I, J, K].shape[2]
         self.klevel = gt_zeros(self.computational_grid, (K,), gt4py_config=self.gt4py_config, dtype_name="int")
         self.klevel[:] = self.klevel.new_tensor(np.arange(0, nk + 1))
-        ad_predicates = ad_predicates or os.environ.get("CS2_AD_PREDICATES", "tl")
+        ad_predicates = ad_predicates or os.environ.get("CS2_AD_PREDICATES", "reference")
         if ad_predicates not in ("tl", "reference"):
             raise ValueError("ad_predicates must be 'tl' or 'reference'")
         self.ad_predicates = ad_predicates

@@ -99,8 +99,11 @@ class NonlinearHostPipeline:
         return s.out.numel() * s.out.element_size()
 
     # ---- the pipeline ------------------------------------------------------------------------
-    def run(self, blocks: Sequence[Dict[str, torch.Tensor]], eta: torch.Tensor | None = None) -> None:
-        """Process all host blocks; on return every block's "out" buffer holds its 10 NL outputs."""
+    def run(self, blocks: Sequence[Dict[str, torch.Tensor]], eta: torch.Tensor | None = None, sync: bool = True) -> None:
+        """Process all host blocks.  With `sync=True` (default) the host waits for the last device-to-host copy, so on
+        return every block's "out" buffer holds its 10 NL outputs and may be read.  With `sync=False` the call only
+        orders the CURRENT stream after the pipeline's streams (stream-ordered, asynchronous): the caller must
+        synchronise (e.g. `torch.cuda.current_stream().synchronize()`) before touching the pinned buffers."""
         eta = eta if eta is not None else self.eta
         if eta is None:
             raise ValueError("eta (the K-field of EtaLevels, from global column 0) is required")
@@ -128,3 +131,5 @@ class NonlinearHostPipeline:
                 slot.ev_free.record(self.s_out)
         for st in (self.s_in, self.s_run, self.s_out):
             cur.wait_stream(st)
+        if sync:
+            self.s_out.synchronize()

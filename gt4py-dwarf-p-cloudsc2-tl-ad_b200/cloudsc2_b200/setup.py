@@ -66,8 +66,8 @@ class HDF5GridOperator:
 def get_state(hdf5_grid_operator: HDF5GridOperator) -> Dict[str, Any]:
     state: Dict[str, Any] = {}
     for name, (h5_name, index, half, units) in FIELD_PROPERTIES.items():
-        if h5_name in hdf5_grid_operator.f:
-            state[name] = hdf5_grid_operator.get_field(h5_name, index, half, units, name)
+        # a missing dataset raises KeyError, like the reference's get_field (setup.py:66-68)
+        state[name] = hdf5_grid_operator.get_field(h5_name, index, half, units, name)
     state["time"] = REFERENCE_TIME
     return state
 
