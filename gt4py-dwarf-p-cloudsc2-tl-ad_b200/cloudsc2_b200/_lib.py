@@ -139,6 +139,11 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p],
     ),
+    "cs2_symmetry_residual_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "cs2_symmetry_residual": (
+        C.c_int,
+        [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -33,15 +33,23 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, experiments: bool = False, out: str = OUT) -> str:
+    """`experiments`: also compile the measured-and-rejected kernel variants of csrc/experiments/ (selected at run time with
+    CS2_NL_PIPE / CS2_NL_SPLIT / CS2_NL_BULK; profiles/README.md).  The shipped library is built without them."""
+    if not force and out == OUT and up_to_date():
         return OUT
-    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), *(["-DCS2_EXPERIMENTS"] if experiments else []),
+           "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--experiments" in sys.argv:  # a second library for A/B runs: CS2_LIB=build/libcloudsc2_b200_experiments.so
+        os.makedirs(os.path.join(HERE, "..", "..", "build"), exist_ok=True)
+        print(build(force=True, verbose="-v" in sys.argv, experiments=True,
+                    out=os.path.normpath(os.path.join(HERE, "..", "..", "build", "libcloudsc2_b200_experiments.so"))))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

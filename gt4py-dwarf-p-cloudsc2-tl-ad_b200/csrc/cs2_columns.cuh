@@ -7,7 +7,6 @@
 #pragma once
 
 #include "cs2_physics.cuh"
-#include "cs2_physics_split.cuh"
 #include "cs2_physics_tl.cuh"
 
 namespace cs2 {
@@ -129,39 +128,6 @@ CS2_HD void column_nl(const DevParams<R>& p, const LevelTables<R>& tab, const NL
     f.o_tnd_ql[off] = o.tnd_ql;
     f.o_tnd_t[off] = o.tnd_t;
     // fluxes shifted one half level down (:395-399)
-    const uint32_t offn = off + uint32_t(S);
-    f.fplsl[offn] = c.rfl;
-    f.fplsn[offn] = c.sfl;
-    f.fhpsl[offn] = -c.rfl * p.RLVTT;
-    f.fhpsn[offn] = -c.sfl * p.RLSTT;
-    aph0 = in.aph1;
-  }
-}
-
-// NL column evaluated through the two half-level functions of the split kernel (cs2_physics_split.cuh); host twin only
-template <class R, class C>
-CS2_HD void column_nl_split(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f, int64_t S, int nlev,
-                            int64_t i) {
-  const int jsel = tropopause_candidate(p, tab, f.t, f.tnd_t, S, i);
-  const int ncand = tab.nw + 1;
-  Carry<R> c{R(0), R(0), R(0)};
-  R aph0 = f.aph[i];
-  f.fhpsl[i] = R(0);
-  f.fhpsn[i] = R(0);
-  for (int k = 0; k < nlev; ++k) {
-    LevelIn<R> in;
-    load_level(f, S, i, k, aph0, in);
-    Mid<R> m;
-    LevelOut<R> o;
-    level_nl_a<R, C>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, m);
-    level_nl_b<R>(p, m, c, o);
-    const uint32_t off = uint32_t(k) * uint32_t(S) + uint32_t(i);
-    f.clc[off] = o.clc;
-    f.covptot[off] = o.covptot;
-    f.o_tnd_q[off] = o.tnd_q;
-    f.o_tnd_qi[off] = o.tnd_qi;
-    f.o_tnd_ql[off] = o.tnd_ql;
-    f.o_tnd_t[off] = o.tnd_t;
     const uint32_t offn = off + uint32_t(S);
     f.fplsl[offn] = c.rfl;
     f.fplsn[offn] = c.sfl;

@@ -120,9 +120,9 @@ __device__ __forceinline__ void dev_column_nl(const DevParams<R>& p, const Level
     if (CKPT) x.defaults();
     level_fwd<R, C, LIN>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     if (CKPT && valid) {
-      const uint32_t plane = uint32_t(nlev) * S;
+      const size_t plane = size_t(nlev) * size_t(S);  // CK_N * plane can exceed 2^32 elements: 64-bit index
 #pragma unroll
-      for (int n = 0; n < CK_N; ++n) ck[uint32_t(n) * plane + off] = x.v[n];
+      for (int n = 0; n < CK_N; ++n) ck[size_t(n) * plane + off] = x.v[n];
     }
     if (valid) {
       f.clc[off] = o.clc;
@@ -407,11 +407,11 @@ __device__ __forceinline__ void dev_column_tl(const DevParams<R>& p, const Level
 // ---------------------------------------------------------------------------------------
 // AD backward.  Streams: [0,16) NL inputs with aph read at level k (not k+1), then the level-entry
 // fluxes fplsl/fplsn[k] written by the forward sweep, the 5 full-level seeds at k and the 4 flux
-// seeds at half level k+1.  The consumed seeds are zeroed by the launcher after the kernel
-// (cudaMemsetAsync on the same stream).  Measured alternatives: zeroing in the kernel right after the
-// load (first version) serialises store-after-load on the same address in L2 and made the kernel 4x
-// slower (profiles/r1c_ad_bwd.md); zeroing in the kernel one level after the copy completed is correct
-// but still 2-5 % slower than the separate memsets (10 more stores per level in a latency-bound loop).
+// seeds at half level k+1.  The reference consumes (zeroes) its seeds; here each thread resets the seeds of the
+// level it consumed CS2_AD_ZERO_LAG iterations earlier from inside the level loop (plain stores off the dependent
+// chain) and the last few levels after the loop -- see the end of dev_column_ad_bwd for the measurements
+// (1.19 ms against 1.29 ms with 10 cudaMemsetAsync after the kernel, which CS2_AD_SEED_MEMSET=1 restores for A/B;
+// zeroing a slot right after its own load serialises in L2 and was 4x slower, profiles/r1c_ad_bwd.md).
 // ---------------------------------------------------------------------------------------
 #ifndef CS2_AD_ZERO_LAG
 #define CS2_AD_ZERO_LAG 4  // the backward sweep resets the seeds of the level it consumed this many iterations ago

@@ -15,8 +15,12 @@
 #include <cstring>
 #include <string>
 
-#include "cs2_bulk_columns.cuh"
-#include "cs2_split_columns.cuh"
+#include "cs2_device_columns.cuh"
+#ifdef CS2_EXPERIMENTS  // measured-and-rejected kernel variants (profiles/README.md); not in the shipped library
+#include "experiments/cs2_bulk_columns.cuh"
+#include "experiments/cs2_pipe_columns.cuh"
+#include "experiments/cs2_split_columns.cuh"
+#endif
 
 namespace {
 
@@ -70,23 +74,29 @@ constexpr int kWideBlock = CS2_WIDE_BLOCK;  // CTA size of the register-hungry T
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
+// Four consecutive columns of one level per thread: four independent FP64 chains (the kernel is bound by the FP64 pipe
+// and its latency: 1-2 exponentials and 3 reciprocals per 24 bytes), two 16-byte loads per input in flight.
 template <class R>
 __global__ void __launch_bounds__(kPointBlock)
 saturation_kernel(const __grid_constant__ cs2::DevParams<R> p, int lphylin, const R* __restrict__ ap,
                   const R* __restrict__ t, R* __restrict__ qsat, int64_t ncol, int64_t S) {
-  // two columns per thread (independent chains for the FP64 pipe), 16-byte accesses
-  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= ncol) return;
   const int64_t off = int64_t(blockIdx.y) * S + i;
-  if (i + 1 < ncol) {
+  if (i + 3 < ncol) {
     using V = typename cs2::Vec2<R>::type;
-    const V a = *reinterpret_cast<const V*>(ap + off), tt = *reinterpret_cast<const V*>(t + off);
-    V q;
-    q.x = cs2::saturation_point<R>(p, lphylin != 0, a.x, tt.x);
-    q.y = cs2::saturation_point<R>(p, lphylin != 0, a.y, tt.y);
-    *reinterpret_cast<V*>(qsat + off) = q;
+    const V a0 = *reinterpret_cast<const V*>(ap + off), a1 = *reinterpret_cast<const V*>(ap + off + 2);
+    const V t0 = *reinterpret_cast<const V*>(t + off), t1 = *reinterpret_cast<const V*>(t + off + 2);
+    const R av[4] = {a0.x, a0.y, a1.x, a1.y}, tv[4] = {t0.x, t0.y, t1.x, t1.y};
+    R q[4];
+    cs2::saturation_points<R, 4>(p, lphylin != 0, av, tv, q);
+    V q0, q1;
+    q0.x = q[0]; q0.y = q[1]; q1.x = q[2]; q1.y = q[3];
+    *reinterpret_cast<V*>(qsat + off) = q0;
+    *reinterpret_cast<V*>(qsat + off + 2) = q1;
   } else {
-    qsat[off] = cs2::saturation_point<R>(p, lphylin != 0, ap[off], t[off]);
+    for (int64_t j = 0; j < 4 && i + j < ncol; ++j)
+      qsat[off + j] = cs2::saturation_point<R>(p, lphylin != 0, ap[off + j], t[off + j]);
   }
 }
 
@@ -143,6 +153,25 @@ nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
                                                jsel_out, ck, cov_out);
 }
 
+#ifdef CS2_EXPERIMENTS
+// default-flag NL (and the AD forward sweep in recompute mode), software-pipelined across two levels
+template <class R>
+#ifdef CS2_PIPE_MAXNREG
+__global__ void __maxnreg__(CS2_PIPE_MAXNREG)
+#else
+__global__ void __launch_bounds__(kColumnBlock, 7)
+#endif
+nl_pipe_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
+               int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out) {
+  __shared__ cs2::Ring<R, cs2::I_NL, kColumnBlock> ring;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < ncol;
+  if (!valid) i = ncol - 1;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_column_nl_pipe<R, kColumnBlock>(p, tab, f, in_s, ring, uint32_t(S), nlev, uint32_t(i), valid, ad_ref != 0, jsel_out);
+}
+
 #ifndef CS2_BULK_BLOCK
 #define CS2_BULK_BLOCK 64
 #endif
@@ -171,6 +200,8 @@ nl_split_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restr
   const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
   cs2::dev_column_nl_split<R, C, NM, kSplitCols>(p, tab, f, in_s, sh, uint32_t(S), nlev, uint32_t(ncol));
 }
+
+#endif  // CS2_EXPERIMENTS
 
 template <class R, class C>
 __global__ void __launch_bounds__(kColumnBlock, 7)
@@ -283,7 +314,7 @@ __global__ void __launch_bounds__(256) dfma_rate_kernel(double* out, int iters, 
 }
 
 // ---- reductions -----------------------------------------------------------------------
-constexpr int kMaxRedFields = 16;
+constexpr int kMaxRedFields = 32;
 struct RedPtrs {
   const void* a[kMaxRedFields];
   const void* b[kMaxRedFields];
@@ -360,21 +391,76 @@ __global__ void taylor_final_kernel(const double2* partial, int nblk, double* su
   }
 }
 
+// norm[i] = SUM_k SUM_f a_f[k, i] * b_f[k, i]: one thread per column, the level loop outside and the (independent) field
+// loads of a level inside, so that 2 * nfields loads are in flight per thread and four accumulators break the FP64 add
+// chain.  A pair with a_f == b_f (norm1 = <TL x, TL x>) is loaded once.
 template <class R>
-__global__ void __launch_bounds__(kColumnBlock)
+__global__ void __launch_bounds__(128)
 symmetry_norm_kernel(const __grid_constant__ RedPtrs f, int nfields, int64_t ncol, int64_t S, int nlevp1,
-                     double* norm) {
+                     double* __restrict__ norm) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= ncol) return;
-  double acc = 0.0;
-  for (int n = 0; n < nfields; ++n) {
-    const R* a = static_cast<const R*>(f.a[n]);
-    const R* b = static_cast<const R*>(f.b[n]);
-    double s = 0.0;
-    for (int k = 0; k < nlevp1; ++k) s += double(a[int64_t(k) * S + i]) * double(b[int64_t(k) * S + i]);
-    acc += s;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  const int nquad = nfields & ~3;
+  for (int k = 0; k < nlevp1; ++k) {
+    const int64_t off = int64_t(k) * S + i;
+    auto prod = [&](int n) {
+      const R* a = static_cast<const R*>(f.a[n]);
+      const R* b = static_cast<const R*>(f.b[n]);
+      const double x = double(a[off]);
+      return x * ((a == b) ? x : double(b[off]));
+    };
+#pragma unroll 2
+    for (int n = 0; n < nquad; n += 4) {
+      const double p0 = prod(n), p1 = prod(n + 1), p2 = prod(n + 2), p3 = prod(n + 3);
+      acc0 += p0; acc1 += p1; acc2 += p2; acc3 += p3;
+    }
+    for (int n = nquad; n < nfields; ++n) acc0 += prod(n);
   }
-  norm[i] = acc;
+  norm[i] = (acc0 + acc1) + (acc2 + acc3);
+}
+
+// Symmetry-test residual (adjoint/validation.py:157-160): norm3[i] = |n1 - n2| / eps if n2 == 0 else |n1 - n2| / (eps * n2),
+// and its maximum over the columns.  Stage 1: per-block maxima (NaN propagates, like numpy's max); stage 2: one warp.
+__global__ void __launch_bounds__(256)
+symmetry_residual_kernel(const double* __restrict__ n1, const double* __restrict__ n2, int64_t ncol, double eps,
+                         double* __restrict__ norm3, double* __restrict__ partial) {
+  double m = -INFINITY;
+  bool nan = false;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < ncol; i += int64_t(gridDim.x) * blockDim.x) {
+    const double a = n1[i], b = n2[i];
+    const double d = fabs(a - b);
+    const double r = (b == 0.0) ? d / eps : d / (eps * b);
+    if (norm3) norm3[i] = r;
+    nan = nan || (r != r);
+    m = fmax(m, r);
+  }
+  __shared__ double sh[8];
+  __shared__ int shn[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  nan = __any_sync(0xffffffffu, nan);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[w] = m; shn[w] = nan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 1; j < 8; ++j) { m = fmax(m, sh[j]); nan = nan || shn[j]; }
+    partial[blockIdx.x] = nan ? NAN : m;
+  }
+}
+
+__global__ void symmetry_residual_final_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  double m = -INFINITY;
+  bool nan = false;
+  for (int b = threadIdx.x; b < nblk; b += 32) {
+    const double v = partial[b];
+    nan = nan || (v != v);
+    m = fmax(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  nan = __any_sync(0xffffffffu, nan);
+  if (threadIdx.x == 0) out[0] = nan ? NAN : m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -441,7 +527,7 @@ template <class R>
 int launch_saturation(const cs2_dims* d, const cs2_params* P, const void* ap, const void* t, void* qsat, cudaStream_t st) {
   if (d->ncol == 0) return CS2_OK;
   const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, 1.0);
-  dim3 grid((unsigned)((d->ncol + 2 * kPointBlock - 1) / (2 * kPointBlock)), (unsigned)d->nlev);
+  dim3 grid((unsigned)((d->ncol + 4 * kPointBlock - 1) / (4 * kPointBlock)), (unsigned)d->nlev);
   saturation_kernel<R><<<grid, kPointBlock, 0, st>>>(p, P->LPHYLIN, static_cast<const R*>(ap), static_cast<const R*>(t),
                                                     static_cast<R*>(qsat), d->ncol, d->ncol_stride);
   return check_cuda(cudaGetLastError(), "saturation launch");
@@ -478,8 +564,14 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
 #define CS2_LAUNCH_NL(E, T)                                                                                         \
   nl_kernel<R, cs2::Cfg<E, T>, false, false><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, \
                                                                             d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr, nullptr)
-  static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;  // experiment switch (profiles/README.md)
+#ifdef CS2_EXPERIMENTS
+  static const bool use_pipe = std::getenv("CS2_NL_PIPE") != nullptr;  // experiment switches (profiles/README.md)
+  static const bool use_bulk = std::getenv("CS2_NL_BULK") != nullptr;
   static const bool use_split = std::getenv("CS2_NL_SPLIT") != nullptr;
+  if (use_pipe && !evap && tetens && !ck && !cov_out && P->RVTMP2 == 0.0) {  // two levels in flight per thread
+    nl_pipe_kernel<R><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev, ad_ref ? 1 : 0, jsel_out);
+    return check_cuda(cudaGetLastError(), "cloudsc2_nl (pipelined) launch");
+  }
   if (use_split && !jsel_out && !evap && d->nlev <= cs2::kSplitMaxLev) {
     const unsigned sgrid = (unsigned)((d->ncol + kSplitCols - 1) / kSplitCols);
 #define CS2_LAUNCH_SPLIT(T, NM)                                                                                  \
@@ -491,10 +583,15 @@ int launch_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
       if (tetens) CS2_LAUNCH_SPLIT(true, cs2::M_N); else CS2_LAUNCH_SPLIT(false, cs2::M_N);
     }
 #undef CS2_LAUNCH_SPLIT
-  } else if (use_bulk && !jsel_out && !evap && tetens)
+    return check_cuda(cudaGetLastError(), "cloudsc2_nl (split) launch");
+  }
+  if (use_bulk && !jsel_out && !evap && tetens) {
     nl_bulk_kernel<R, cs2::Cfg<false, true>><<<(unsigned)((d->ncol + kBulkBlock - 1) / kBulkBlock), kBulkBlock, 0, st>>>(
         p, tables, nf, ns, d->ncol, d->ncol_stride, d->nlev);
-  else if (cov_out)  // AD forward sweep with the evaporation branch (recompute mode): also stores the overlap carry
+    return check_cuda(cudaGetLastError(), "cloudsc2_nl (bulk) launch");
+  }
+#endif
+  if (cov_out)  // AD forward sweep with the evaporation branch (recompute mode): also stores the overlap carry
     nl_kernel<R, cs2::Cfg<true, true>, false, true><<<grid, kColumnBlock, 0, st>>>(p, tables, nf, ns, d->ncol, d->ncol_stride,
                                                                                    d->nlev, ad_ref ? 1 : 0, jsel_out, nullptr, cov_out);
   else if (ck)  // AD forward sweep with checkpointing of the transcendentals (evaporation off, Tetens path)
@@ -859,7 +956,7 @@ int cs2_taylor_sums(const cs2_dims* dims, int32_t nfields, const void* const* a_
                     const void* const* c_dev, double* sums_dev, void* scratch_dev, size_t scratch_bytes,
                     void* stream) {
   if (int rc = check_dims(dims)) return rc;
-  if (nfields < 1 || nfields > kMaxRedFields) return fail(CS2_ERR_BAD_DIMS, "taylor_sums: nfields outside [1, 16]");
+  if (nfields < 1 || nfields > 16) return fail(CS2_ERR_BAD_DIMS, "taylor_sums: nfields outside [1, 16]");
   if (!a_dev || !sums_dev || !scratch_dev) return fail(CS2_ERR_NULL_POINTER, "taylor_sums: NULL argument");
   if (scratch_bytes < cs2_taylor_scratch_bytes(dims, nfields)) return fail(CS2_ERR_WORKSPACE, "taylor_sums: scratch too small");
   RedPtrs f;
@@ -904,7 +1001,7 @@ int cs2_taylor_nl_sums(const cs2_dims* dims, const cs2_params* params, double dt
 int cs2_symmetry_norms(const cs2_dims* dims, int32_t nfields, const void* const* a_dev, const void* const* b_dev,
                        double* norm_dev, void* stream) {
   if (int rc = check_dims(dims)) return rc;
-  if (nfields < 1 || nfields > kMaxRedFields) return fail(CS2_ERR_BAD_DIMS, "symmetry_norms: nfields outside [1, 16]");
+  if (nfields < 1 || nfields > kMaxRedFields) return fail(CS2_ERR_BAD_DIMS, "symmetry_norms: nfields outside [1, 32]");
   if (!a_dev || !b_dev || !norm_dev) return fail(CS2_ERR_NULL_POINTER, "symmetry_norms: NULL argument");
   if (int rc = check_ptrs(a_dev, nfields, "symmetry_norms a")) return rc;
   if (int rc = check_ptrs(b_dev, nfields, "symmetry_norms b")) return rc;
@@ -915,12 +1012,35 @@ int cs2_symmetry_norms(const cs2_dims* dims, int32_t nfields, const void* const*
     f.b[n] = n < nfields ? b_dev[n] : nullptr;
     f.c[n] = nullptr;
   }
-  const unsigned grid = (unsigned)((dims->ncol + kColumnBlock - 1) / kColumnBlock);
+  const unsigned grid = (unsigned)((dims->ncol + 127) / 128);
   if (dims->dtype == CS2_F64)
-    symmetry_norm_kernel<double><<<grid, kColumnBlock, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
+    symmetry_norm_kernel<double><<<grid, 128, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
   else
-    symmetry_norm_kernel<float><<<grid, kColumnBlock, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
+    symmetry_norm_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(f, nfields, dims->ncol, dims->ncol_stride, dims->nlev + 1, norm_dev);
   return check_cuda(cudaGetLastError(), "symmetry norm launch");
+}
+
+static int residual_blocks(int64_t ncol) {
+  int64_t nb = (ncol + 255) / 256;
+  if (nb < 1) nb = 1;
+  if (nb > 148 * 4) nb = 148 * 4;
+  return int(nb);
+}
+
+size_t cs2_symmetry_residual_scratch_bytes(int64_t ncol) { return size_t(residual_blocks(ncol)) * sizeof(double); }
+
+int cs2_symmetry_residual(int64_t ncol, const double* norm1_dev, const double* norm2_dev, double eps, double* norm3_dev,
+                          double* max_dev, void* scratch_dev, size_t scratch_bytes, void* stream) {
+  if (ncol < 0) return fail(CS2_ERR_BAD_DIMS, "symmetry_residual: ncol < 0");
+  if (!norm1_dev || !norm2_dev || !max_dev || !scratch_dev) return fail(CS2_ERR_NULL_POINTER, "symmetry_residual: NULL argument");
+  if (!(eps > 0.0)) return fail(CS2_ERR_BAD_DIMS, "symmetry_residual: eps must be positive");
+  if (scratch_bytes < cs2_symmetry_residual_scratch_bytes(ncol)) return fail(CS2_ERR_WORKSPACE, "symmetry_residual: scratch too small");
+  const int nb = residual_blocks(ncol);
+  symmetry_residual_kernel<<<nb, 256, 0, as_stream(stream)>>>(norm1_dev, norm2_dev, ncol, eps, norm3_dev,
+                                                              static_cast<double*>(scratch_dev));
+  if (int rc = check_cuda(cudaGetLastError(), "symmetry residual launch")) return rc;
+  symmetry_residual_final_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<const double*>(scratch_dev), nb, max_dev);
+  return check_cuda(cudaGetLastError(), "symmetry residual final launch");
 }
 
 }  // extern "C"

@@ -170,6 +170,41 @@ CS2_HD R saturation_point(const DevParams<R>& p, bool lphylin, R ap, R t) {
   return qs * rcp(R(1) - p.RETV * qs);
 }
 
+// N points at once (the saturation kernel): same statements as saturation_point, the exponentials of the N points in
+// lockstep per phase (a phase no point needs is skipped: at one level the columns of a thread are all cold, all warm or
+// all mixed), and qs / (1 - RETV qs) = foeew / (ap - RETV foeew) where the clip does not bind -- one reciprocal for the
+// last two divisions (saturation.py:35,42; the clip test foeew / ap > QMAX is foeew > QMAX ap, ap > 0).
+template <class R, int N>
+CS2_HD void saturation_points(const DevParams<R>& p, bool lphylin, const R (&ap)[N], const R (&t)[N], R (&qsat)[N]) {
+  R alfa[N], xl[N], xi[N], el[N], ei[N];
+  bool need_l = false, need_i = false;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    alfa[n] = (lphylin || p.kflag != 1) ? foealfa(p, t[n]) : foealfcu(p, t[n]);
+    const R dtt = t[n] - p.RTT;
+    xl[n] = p.R3LES * dtt * rcp(t[n] - p.R4LES);
+    xi[n] = p.R3IES * dtt * rcp(t[n] - p.R4IES);
+    need_l = need_l || (alfa[n] > R(0));
+    need_i = need_i || (alfa[n] < R(1));
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) el[n] = ei[n] = R(0);
+  if (need_l) exp_batch<N>(xl, el);
+  if (need_i) exp_batch<N>(xi, ei);
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    // a phase with weight exactly 0 contributes an exact 0, as in saturation_point (alfa is 0 below RTICE, 1 above RTWAT)
+    const R wl = (alfa[n] > R(0)) ? el[n] : R(0), wi = (alfa[n] < R(1)) ? ei[n] : R(0);
+    R foeew;
+    if (lphylin)
+      foeew = alfa[n] * (p.R2ES * wl) + (R(1) - alfa[n]) * (p.R2ES * wi);
+    else
+      foeew = p.R2ES * (alfa[n] * wl + (R(1) - alfa[n]) * wi);
+    const bool clip = foeew > p.QMAX * ap[n];
+    qsat[n] = clip ? p.qsat_clip : foeew * rcp(ap[n] - p.RETV * foeew);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // saturation adjustment step (nonlinear/_stencils/cuadjtqs.py:22-35)
 // ---------------------------------------------------------------------------------------

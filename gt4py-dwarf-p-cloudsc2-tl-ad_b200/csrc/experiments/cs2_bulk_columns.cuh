@@ -6,7 +6,7 @@
 // __syncthreads per level (the buffer a bulk copy overwrites must have been read by every thread).
 #pragma once
 
-#include "cs2_device_columns.cuh"
+#include "../cs2_device_columns.cuh"
 
 namespace cs2 {
 

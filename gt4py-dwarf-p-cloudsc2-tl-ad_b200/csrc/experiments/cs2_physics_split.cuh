@@ -15,7 +15,7 @@
 // walks per level is half as long.  Evaporation branch off only (the default configuration).
 #pragma once
 
-#include "cs2_physics.cuh"
+#include "../cs2_physics.cuh"
 
 namespace cs2 {
 

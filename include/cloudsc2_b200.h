@@ -256,7 +256,12 @@ int cs2_taylor_nl_sums(const cs2_dims* dims, const cs2_params* params, double dt
  *   sums_dev: 2*nfields doubles, NOT zeroed by the call (so shards can be accumulated);
  *   scratch_dev: cs2_taylor_scratch_bytes(dims, nfields) bytes.
  * cs2_symmetry_norms -- SymmetryTest.get_norm1/get_norm2 (adjoint/validation.py:167-215):
- *   norm_dev[i] = SUM_k SUM_f a_f[k,i] * b_f[k,i] per column (fp64).
+ *   norm_dev[i] = SUM_k SUM_f a_f[k,i] * b_f[k,i] per column (fp64), up to 32 field pairs per call (norm2 has 16);
+ *   a pair with a_f == b_f is read once.
+ * cs2_symmetry_residual -- SymmetryTest.__call__ (adjoint/validation.py:157-165):
+ *   norm3_dev[i] = |n1 - n2| / eps where n2 == 0, |n1 - n2| / (eps * n2) elsewhere (norm3_dev may be NULL), and
+ *   max_dev[0] = max_i norm3[i] (NaN if any norm3 is NaN, -inf for ncol == 0) -- the one double a sharded run
+ *   all-reduces (MAX).  scratch_dev: cs2_symmetry_residual_scratch_bytes(ncol) bytes.  Deterministic.
  * ------------------------------------------------------------------------------------- */
 size_t cs2_taylor_scratch_bytes(const cs2_dims* dims, int32_t nfields);
 int cs2_taylor_sums(const cs2_dims* dims, int32_t nfields, const void* const* a_dev,
@@ -264,6 +269,10 @@ int cs2_taylor_sums(const cs2_dims* dims, int32_t nfields, const void* const* a_
                     void* scratch_dev, size_t scratch_bytes, void* stream);
 int cs2_symmetry_norms(const cs2_dims* dims, int32_t nfields, const void* const* a_dev,
                        const void* const* b_dev, double* norm_dev, void* stream);
+size_t cs2_symmetry_residual_scratch_bytes(int64_t ncol);
+int cs2_symmetry_residual(int64_t ncol, const double* norm1_dev, const double* norm2_dev, double eps,
+                          double* norm3_dev, double* max_dev, void* scratch_dev, size_t scratch_bytes,
+                          void* stream);
 
 #ifdef __cplusplus
 }

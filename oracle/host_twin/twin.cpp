@@ -13,6 +13,8 @@
 #include <cstring>
 
 #include "../../gt4py-dwarf-p-cloudsc2-tl-ad_b200/csrc/cs2_columns.cuh"
+// the level functions of the kernel experiments stay under test here although the shipped library does not contain them
+#include "../../gt4py-dwarf-p-cloudsc2-tl-ad_b200/csrc/experiments/cs2_experiment_columns.cuh"
 
 namespace {
 template <class R>
@@ -41,6 +43,15 @@ void run_nl_split(const cs2_dims* d, const cs2_params* P, double dt, const void*
     if (tetens) cs2::column_nl_split<R, cs2::Cfg<false, true>>(p, tab, nf, d->ncol_stride, d->nlev, i);
     else cs2::column_nl_split<R, cs2::Cfg<false, false>>(p, tab, nf, d->ncol_stride, d->nlev, i);
   }
+}
+
+template <class R>
+void run_nl_pipe(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f, bool ad_ref) {
+  const cs2::DevParams<R> p = cs2::make_dev_params<R>(*P, dt);
+  const cs2::NLFields<R> nf = cs2::make_nl_fields<R>(*f);
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < d->ncol; ++i) cs2::column_nl_pipe<R>(p, tab, nf, d->ncol_stride, d->nlev, i, ad_ref, nullptr);
 }
 
 template <class R>
@@ -96,11 +107,20 @@ void run_sat(const cs2_dims* d, const cs2_params* P, const void* ap, const void*
   const R* tt = (const R*)t;
   R* q = (R*)qsat;
 #pragma omp parallel for schedule(static)
-  for (int k = 0; k < d->nlev; ++k)
-    for (int64_t i = 0; i < d->ncol; ++i) {
+  for (int k = 0; k < d->nlev; ++k) {
+    int64_t i = 0;
+    for (; i + 3 < d->ncol; i += 4) {  // four points at once, as a thread of saturation_kernel does
+      const int64_t o = int64_t(k) * d->ncol_stride + i;
+      const R av[4] = {a[o], a[o + 1], a[o + 2], a[o + 3]}, tv[4] = {tt[o], tt[o + 1], tt[o + 2], tt[o + 3]};
+      R qv[4];
+      cs2::saturation_points<R, 4>(p, P->LPHYLIN != 0, av, tv, qv);
+      for (int j = 0; j < 4; ++j) q[o + j] = qv[j];
+    }
+    for (; i < d->ncol; ++i) {
       const int64_t o = int64_t(k) * d->ncol_stride + i;
       q[o] = cs2::saturation_point<R>(p, P->LPHYLIN != 0, a[o], tt[o]);
     }
+  }
 }
 }  // namespace
 
@@ -117,6 +137,13 @@ int twin_nl(const cs2_dims* d, const cs2_params* P, double dt, const void* table
 int twin_nl_split(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f) {
   if (P->LEVAPLS2 || P->LDRAIN1D) return 1;
   if (d->dtype == CS2_F64) run_nl_split<double>(d, P, dt, tables, f); else run_nl_split<float>(d, P, dt, tables, f);
+  return 0;
+}
+// the software-pipelined level function of the default-flag NL kernel (cs2_physics_pipe.cuh); default flags only
+int twin_nl_pipe(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f, int ad_ref) {
+  if (P->LEVAPLS2 || P->LDRAIN1D || !P->LPHYLIN || P->RVTMP2 != 0.0) return 1;
+  if (d->dtype == CS2_F64) run_nl_pipe<double>(d, P, dt, tables, f, ad_ref != 0);
+  else run_nl_pipe<float>(d, P, dt, tables, f, ad_ref != 0);
   return 0;
 }
 int twin_tl(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* f,

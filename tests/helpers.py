@@ -334,15 +334,20 @@ def twin_saturation(ap, t, P):
     return h.get("qsat")
 
 
-def twin_nl(s, dt, P, split=False):
-    """`split`: through the two half-level functions of the split NL kernel (cs2_physics_split.cuh)."""
+def twin_nl(s, dt, P, split=False, pipe=False, ad_ref=False):
+    """`split`: through the two half-level functions of the split NL kernel (cs2_physics_split.cuh);
+    `pipe`: through the software-pipelined level function of the default NL kernel (cs2_physics_pipe.cuh)."""
     nlev, ncol = s["f_ap"].shape[0] - 1, s["f_ap"].shape[1]
     h = HostFields(ncol, nlev, s["f_ap"].dtype)
     f = _nl_struct(h, s)
     tab = level_tables(P, s["f_eta"], nlev, h.dtype)
     params, dims = _lib.make_params(P), h.dims()
-    fn = twin().twin_nl_split if split else twin().twin_nl
-    rc = fn(C.byref(dims), C.byref(params), C.c_double(dt), C.c_void_p(tab.ctypes.data), C.byref(f))
+    if pipe:
+        rc = twin().twin_nl_pipe(C.byref(dims), C.byref(params), C.c_double(dt), C.c_void_p(tab.ctypes.data), C.byref(f),
+                                 C.c_int(1 if ad_ref else 0))
+    else:
+        fn = twin().twin_nl_split if split else twin().twin_nl
+        rc = fn(C.byref(dims), C.byref(params), C.c_double(dt), C.c_void_p(tab.ctypes.data), C.byref(f))
     assert rc == 0
     return _collect_nl(h)
 

@@ -519,41 +519,3 @@ def test_other_level_counts_and_timesteps(nz, dt):
     # the reference's 1e4-eps criterion is calibrated on 137 levels; on coarse columns the inner products are less
     # well conditioned, so compare with what the oracle itself achieves
     assert out["symmetry_norm3_max"] < max(1e4, 10 * n3.max())
-
-
-def test_tma_bulk_copy_variant_of_nl_matches_oracle():
-    """`CS2_NL_BULK=1` selects the cp.async.bulk (TMA) staging variant of the NL kernel (measured alternative, not the
-    default): same results as the oracle, including a ragged last CTA."""
-    import subprocess
-    import sys
-
-    code = (
-        "import sys, numpy as np; sys.path[:0]=[%r, %r, %r];"
-        "import helpers as H, gpu_harness as G;"
-        "out=G.run_components(block='base', dtype=np.float64, ncol=1001, nl_only=True);"
-        "P=H.externals(); s=H.with_diagnostics(H.make_state('base', np.float64, 1001), P);"
-        "tn,dg=H.onp.cloudsc2_nl(s,H.DT,P);"
-        "H.assert_fields_close(out['tends_nl'],tn,1e-12); H.assert_fields_close(out['diags_nl'],dg,1e-12); print('BULK_OK')"
-    ) % (os.path.join(H.ROOT, "tests"), H.ROOT, H.PKG_DIR)
-    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CS2_NL_BULK="1"), capture_output=True, text=True,
-                         timeout=600)
-    assert res.returncode == 0 and "BULK_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
-
-
-def test_two_warp_split_variant_of_nl_matches_oracle():
-    """`CS2_NL_SPLIT=1` selects the two-warps-per-column NL kernel (level_nl_a / level_nl_b handed over through shared memory;
-    measured alternative, not the default): same results as the oracle, including a ragged last CTA."""
-    import subprocess
-    import sys
-
-    code = (
-        "import sys, numpy as np; sys.path[:0]=[%r, %r, %r];"
-        "import helpers as H, gpu_harness as G;"
-        "out=G.run_components(block='base', dtype=np.float64, ncol=1001, nl_only=True);"
-        "P=H.externals(); s=H.with_diagnostics(H.make_state('base', np.float64, 1001), P);"
-        "tn,dg=H.onp.cloudsc2_nl(s,H.DT,P);"
-        "H.assert_fields_close(out['tends_nl'],tn,1e-12); H.assert_fields_close(out['diags_nl'],dg,1e-12); print('SPLIT_OK')"
-    ) % (os.path.join(H.ROOT, "tests"), H.ROOT, H.PKG_DIR)
-    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CS2_NL_SPLIT="1"), capture_output=True, text=True,
-                         timeout=600)
-    assert res.returncode == 0 and "SPLIT_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
