@@ -15,8 +15,9 @@ from cloudsc2_b200.physics.common.diagnostics import EtaLevels
 FLOPS_PER_100_COLUMNS = 12482329  # hard-coded CLOUDSC HPM count behind the reference's "MFLOPS" 
 
 
-def problem(config) -> Tuple[ComputationalGrid, Dict[str, Any], timedelta, Dict[str, Any], bool]:
-    """(grid, state incl. f_eta, timestep, parameter sets, from_file)."""
+def problem(config, block: str = "base") -> Tuple[ComputationalGrid, Dict[str, Any], timedelta, Dict[str, Any], bool]:
+    """(grid, state incl. f_eta, timestep, parameter sets, from_file).  `block`: which seeded synthetic block stands in
+    for a missing input file ("base": warm and cold columns; "cold": all-cold columns like the reference's shipped input)."""
     cfg = config.gt4py_config
     from_file = bool(config.input_file) and os.path.exists(config.input_file)
     if from_file:
@@ -32,7 +33,7 @@ def problem(config) -> Tuple[ComputationalGrid, Dict[str, Any], timedelta, Dict[
     else:
         nx = config.num_cols or synthetic.KLON
         grid = ComputationalGrid(GridConfig(nx=nx, ny=1, nz=synthetic.KLEV))
-        state = setup.get_synthetic_state(grid, gt4py_config=cfg)
+        state = setup.get_synthetic_state(grid, gt4py_config=cfg, block=block)
         dt = iox.DEFAULT_TIMESTEP
         params = iox.ifs_defaults()
     state.update(EtaLevels(grid, enable_checks=config.sympl_enable_checks, gt4py_config=cfg)(state))

@@ -8,6 +8,7 @@ hundred bytes per test, plus the broadcast of the 137 eta values derived from GL
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Tuple
 
@@ -22,8 +23,23 @@ def shard_columns(nx_global: int, rank: int, world_size: int) -> Tuple[int, int]
     return start, start + base + (1 if rank < rem else 0)
 
 
+_local_only = 0
+
+
 def is_distributed() -> bool:
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return _local_only == 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside this context the collectives below are no-ops although a process group exists: a rank runs a complete,
+    un-sharded control problem next to the sharded one (bench.py's config-5 check, tests/dist_gpu_worker.py)."""
+    global _local_only
+    _local_only += 1
+    try:
+        yield
+    finally:
+        _local_only -= 1
 
 
 def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:

@@ -27,7 +27,11 @@ from .physics.nonlinear.microphysics import Cloudsc2NL
 
 # packed order of a block's input / output planes (f_qsat is produced on the device, not copied in)
 IN_NAMES = tuple(f"f_{n}" for n in NL_INPUTS if n != "qsat")
-OUT_NAMES = tuple(f"f_{n}" for n in NL_TENDENCIES) + tuple(f"f_{n}" for n in NL_DIAGNOSTICS)
+# f_covptot last: without the precipitation-evaporation branch (LEVAPLS2 / LDRAIN1D off, the default) the stencil writes
+# an identical 0 to it (nonlinear/_stencils/cloudsc2.py:138), so its plane is not copied back (10 % of the D2H traffic):
+# the host plane is zero from its allocation on
+OUT_NAMES = (tuple(f"f_{n}" for n in NL_TENDENCIES) + tuple(f"f_{n}" for n in NL_DIAGNOSTICS if n != "covptot")
+             + ("f_covptot",))
 
 
 class _Slot:
@@ -66,6 +70,8 @@ class NonlinearHostPipeline:
         self.saturation = Saturation(self.grid, 1, True, p["yoethf"], p["yomcst"], gt4py_config=gt4py_config)
         self.cloudsc2_nl = Cloudsc2NL(self.grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"],
                                       p["yrphnc"], gt4py_config=gt4py_config)
+        self.covptot_is_zero = not bool(getattr(p["yrphnc"], "LEVAPLS2", False))  # ldrain1d is False here
+        self.nout_copied = len(OUT_NAMES) - 1 if self.covptot_is_zero else len(OUT_NAMES)
         self.slots = [_Slot(self.grid, gt4py_config, self.device) for _ in range(nslots)]
         self.s_in, self.s_run, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         self.eta = None if eta is None else torch.as_tensor(np.asarray(eta), dtype=torch_dtype(gt4py_config.dtypes.float))
@@ -96,7 +102,7 @@ class NonlinearHostPipeline:
     @property
     def d2h_bytes_per_block(self) -> int:
         s = self.slots[0]
-        return s.out.numel() * s.out.element_size()
+        return s.out[: self.nout_copied].numel() * s.out.element_size()
 
     # ---- the pipeline ------------------------------------------------------------------------
     def run(self, blocks: Sequence[Dict[str, torch.Tensor]], eta: torch.Tensor | None = None, sync: bool = True) -> None:
@@ -127,7 +133,7 @@ class NonlinearHostPipeline:
                 self.launches += 2
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot.ev_done)
-                blk["out"].copy_(slot.out, non_blocking=True)
+                blk["out"][: self.nout_copied].copy_(slot.out[: self.nout_copied], non_blocking=True)
                 slot.ev_free.record(self.s_out)
         for st in (self.s_in, self.s_run, self.s_out):
             cur.wait_stream(st)

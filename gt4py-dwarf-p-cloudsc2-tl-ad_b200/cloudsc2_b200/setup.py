@@ -86,9 +86,28 @@ def state_from_arrays(arrays: Dict[str, np.ndarray], computational_grid: Computa
 
 def get_synthetic_state(computational_grid: ComputationalGrid, *, gt4py_config: GT4PyConfig, block: str = "base",
                         seed: int = 0, column_offset: int = 0) -> Dict[str, Any]:
-    """Synthetic state tiled from the 100-column block; `column_offset` = first global column of a shard."""
+    """Synthetic state tiled from the 100-column block (column i <- i mod 100, like `--num-cols` tiles input.h5);
+    `column_offset` = first global column of a shard.  The block is uploaded once and tiled ON THE DEVICE, so a
+    1 M-column state costs no 20 GB of host arrays."""
+    import torch
+
+    from .framework.storage import default_device, torch_dtype
+
     nz, nx = computational_grid.nz, computational_grid.nx
     blk = synthetic.base_block(nz=nz, seed=seed) if block == "base" else synthetic.cold_block(nz=nz, seed=seed + 1)
-    cols = (np.arange(nx) + column_offset) % synthetic.KLON
-    arrays = {k: v[:, cols] for k, v in blk.items()}
-    return state_from_arrays(arrays, computational_grid, gt4py_config=gt4py_config)
+    dev = default_device(gt4py_config)
+    if dev.type != "cuda" or nx <= 4 * synthetic.KLON:
+        cols = (np.arange(nx) + column_offset) % synthetic.KLON
+        return state_from_arrays({k: v[:, cols] for k, v in blk.items()}, computational_grid, gt4py_config=gt4py_config)
+    cols = (torch.arange(nx, device=dev) + column_offset) % synthetic.KLON
+    dt = torch_dtype(gt4py_config.dtypes.float)
+    state: Dict[str, Any] = {}
+    for name, arr in blk.items():
+        dims = (I, J, K - 1 / 2) if name == "f_aph" else (I, J, K)
+        units = FIELD_PROPERTIES[name][3] if name in FIELD_PROPERTIES else ""
+        fld = zeros(computational_grid, dims, gt4py_config=gt4py_config, units=units, name=name)
+        src = torch.as_tensor(np.ascontiguousarray(arr), device=dev).to(dt)  # host rounding to the field dtype
+        fld.buffer[: src.shape[0], :nx].copy_(src.index_select(1, cols))
+        state[name] = fld
+    state["time"] = REFERENCE_TIME
+    return state

@@ -261,6 +261,35 @@ def test_reductions_match_numpy():
         n = symmetry_norms(flds[:3], flds[3:]).cpu().numpy()
         refn = sum(np.sum(arrs[i].astype(np.float64) * arrs[i + 3], axis=0) for i in range(3))
         np.testing.assert_allclose(n, refn, rtol=1e-9, atol=1e-9)
+        # a == b pairs (norm1 = <TL x, TL x>) are read once; 5 pairs = one quad + one left over
+        n = symmetry_norms(flds[:5], flds[:5]).cpu().numpy()
+        refn = sum(np.sum(arrs[i].astype(np.float64) ** 2, axis=0) for i in range(5))
+        np.testing.assert_allclose(n, refn, rtol=1e-9, atol=1e-9)
+
+
+def test_symmetry_residual_matches_numpy_incl_zero_negative_and_nan():
+    """cs2_symmetry_residual = adjoint/validation.py:157-160 + the max over columns, NaN propagating like numpy's max."""
+    from cloudsc2_b200.reductions import SymmetryResidual
+
+    rng = np.random.default_rng(5)
+    eps = float(np.finfo(np.float64).eps)
+    for n in (1, 31, 1000, 70001):
+        n1 = rng.normal(size=n)
+        n2 = n1 * (1 + 1e-13 * rng.normal(size=n))
+        n2[:: 7] = 0.0          # norm2 == 0 -> |n1 - n2| / eps
+        n2[1:: 11] *= -1.0      # negative norm2 -> negative norm3, as in the reference expression
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref = np.where(n2 == 0, np.abs(n1 - n2) / eps, np.abs(n1 - n2) / (eps * n2))
+        res = SymmetryResidual()
+        n3, mx = res(torch.as_tensor(n1, device="cuda"), torch.as_tensor(n2, device="cuda"), eps)
+        np.testing.assert_allclose(n3.cpu().numpy(), ref, rtol=1e-14)
+        assert float(mx.item()) == ref.max()
+        if n > 31:
+            n1[n // 2] = np.nan
+            _, mx = res(torch.as_tensor(n1, device="cuda"), torch.as_tensor(n2, device="cuda"), eps)
+            assert np.isnan(float(mx.item()))
+    _, mx = SymmetryResidual()(torch.empty(0, dtype=torch.float64, device="cuda"), torch.empty(0, dtype=torch.float64, device="cuda"), eps)
+    assert float(mx.item()) == -np.inf  # an empty shard never wins the MAX all-reduce
 
 
 def test_drivers_run_end_to_end(tmp_path):
@@ -271,7 +300,8 @@ def test_drivers_run_end_to_end(tmp_path):
     csv_path = tmp_path / "perf.csv"
     for mod, extra in (("drivers.run_nonlinear", ["--num-cols", "300", "--num-runs", "2", "--output-csv-file", str(csv_path)]),
                        ("drivers.run_taylor_test", ["--num-cols", "300"]),
-                       ("drivers.run_symmetry_test", ["--num-cols", "300"])):
+                       ("drivers.run_symmetry_test", ["--num-cols", "300"]),  # literal AD predicates, all-cold block
+                       ("drivers.run_symmetry_test", ["--num-cols", "300", "--synthetic-block", "base", "--ad-predicates", "tl"])):
         res = subprocess.run([sys.executable, "-m", mod, *extra], cwd=H.ROOT, capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
         if mod.endswith("nonlinear"):
@@ -281,6 +311,10 @@ def test_drivers_run_end_to_end(tmp_path):
         if mod.endswith("symmetry_test"):
             assert "The symmetry test passed. HOORAY!" in res.stdout
     assert csv_path.read_text().count("nl-b200") == 1
+    # the literal predicates on columns that cross RTT inside a level: the reference's own test fails, and so does the drop-in
+    res = subprocess.run([sys.executable, "-m", "drivers.run_symmetry_test", "--num-cols", "300", "--synthetic-block", "base"],
+                         cwd=H.ROOT, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 1 and "The symmetry test failed." in res.stdout and "AD branch predicates: 'reference'" in res.stdout
 
 
 def test_multi_gpu_sharded_taylor_and_symmetry():
