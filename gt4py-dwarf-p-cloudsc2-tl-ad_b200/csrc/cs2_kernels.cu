@@ -1032,7 +1032,8 @@ size_t cs2_symmetry_residual_scratch_bytes(int64_t ncol) { return size_t(residua
 int cs2_symmetry_residual(int64_t ncol, const double* norm1_dev, const double* norm2_dev, double eps, double* norm3_dev,
                           double* max_dev, void* scratch_dev, size_t scratch_bytes, void* stream) {
   if (ncol < 0) return fail(CS2_ERR_BAD_DIMS, "symmetry_residual: ncol < 0");
-  if (!norm1_dev || !norm2_dev || !max_dev || !scratch_dev) return fail(CS2_ERR_NULL_POINTER, "symmetry_residual: NULL argument");
+  if (!max_dev || !scratch_dev || (ncol > 0 && (!norm1_dev || !norm2_dev)))
+    return fail(CS2_ERR_NULL_POINTER, "symmetry_residual: NULL argument");
   if (!(eps > 0.0)) return fail(CS2_ERR_BAD_DIMS, "symmetry_residual: eps must be positive");
   if (scratch_bytes < cs2_symmetry_residual_scratch_bytes(ncol)) return fail(CS2_ERR_WORKSPACE, "symmetry_residual: scratch too small");
   const int nb = residual_blocks(ncol);
