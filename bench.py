@@ -708,10 +708,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE line, the JSON record: whatever libraries write to file descriptor 1 while the run is set
+    # up (e.g. "NCCL version ..." at communicator creation) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

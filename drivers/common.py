@@ -60,3 +60,27 @@ def write_performance_to_csv(path, host_name, precision, variant, num_cols, num_
 
         w.writerow([datetime.date.today().strftime("%Y%m%d"), host_name, precision, variant, num_cols, num_threads, nproma,
                     num_runs, runtime_mean, runtime_stddev, mflops_mean, mflops_stddev])
+
+
+def write_stencils_performance_to_csv(path, host_name, precision, variant, num_cols, num_threads, num_runs, exec_info,
+                                      key_patterns=("cloudsc", "saturation")) -> None:
+    """Per-stencil timings (reference drivers/run_nonlinear.py:221-232 -> ifs_physics_common.output.
+    write_stencils_performance_to_csv, whose exact column set is not in the reference tree): one row per stencil whose
+    name contains one of `key_patterns`, with the number of calls and the device time GT4Py would report as
+    `exec_info[<stencil>]["total_run_time"]` (here: CUDA events around the kernel launches of the stencil)."""
+    from cloudsc2_b200.framework.stencil import resolve_exec_info
+
+    import datetime
+
+    new = not os.path.exists(path)
+    with open(path, "a", newline="") as fh:
+        w = csv.writer(fh, delimiter=",")
+        if new:
+            w.writerow(["date", "host", "precision", "variant", "num_cols", "num_threads", "num_runs", "stencil", "ncalls",
+                        "total_run_time_ms", "run_time_per_call_ms"])
+        for name, rec in sorted(resolve_exec_info(exec_info).items()):
+            if not any(pat in name for pat in key_patterns):
+                continue
+            total_ms = rec["total_run_time"] * 1e3
+            w.writerow([datetime.date.today().strftime("%Y%m%d"), host_name, precision, variant, num_cols, num_threads,
+                        num_runs, name, rec["ncalls"], total_ms, total_ms / max(rec["ncalls"], 1)])

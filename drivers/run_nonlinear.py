@@ -12,7 +12,7 @@ import click
 import numpy as np
 
 from .config import DEFAULT_CONFIG, DEFAULT_IO_CONFIG, ROOT
-from .common import FLOPS_PER_100_COLUMNS, problem, stats, write_performance_to_csv
+from .common import FLOPS_PER_100_COLUMNS, problem, stats, write_performance_to_csv, write_stencils_performance_to_csv
 from cloudsc2_b200.framework.stencil import resolve_exec_info
 from cloudsc2_b200.framework.timing import Timer, timing
 from cloudsc2_b200.physics.common.saturation import Saturation
@@ -70,10 +70,15 @@ def core(config, io_config):
         print("\n== Validation:")
         out = {k: v.numpy() for k, v in {**tends, **diags}.items() if hasattr(v, "numpy")}
         if from_file:
-            g = np.load(config.reference_file)
+            if config.reference_file.endswith(".h5"):  # a golden file in the reference's HDF5 form (data/reference_*.h5)
+                from cloudsc2_b200.h5lite import File
+
+                g = File(config.reference_file)
+            else:
+                g = np.load(config.reference_file)
             nz, klon = grid.nz, int(g["KLON"][0])
             cols = np.arange(nx) % klon
-            pad = lambda a: np.vstack([a, np.zeros((1, a.shape[1]))])  # noqa: E731
+            pad = lambda a: np.vstack([a, np.zeros((1, a.shape[1]))]) if a.shape[0] == nz else a  # noqa: E731
             ref = {"f_clc": pad(g["PCLC"])[:, cols], "f_fplsn": g["PFPLSN"][:, cols], "f_fhpsn": g["PFHPSN"][:, cols],
                    "f_fplsl": g["PFPLSL"][:, cols], "f_fhpsl": g["PFHPSL"][:, cols], "f_t": pad(g["TENDENCY_LOC_T"])[:, cols],
                    "f_q": pad(g["TENDENCY_LOC_Q"])[:, cols], "f_ql": pad(g["TENDENCY_LOC_CLD"][0])[:, cols],
@@ -89,7 +94,9 @@ def core(config, io_config):
             label = "fixture"
         ok = validate(out, ref, config.atol, config.rtol, label)
         print("validation passed" if ok else "validation FAILED")
-    return config
+    from dataclasses import replace
+
+    return replace(config, num_cols=nx)
 
 
 @click.command()
@@ -101,20 +108,28 @@ def core(config, io_config):
 @click.option("--precision", type=click.Choice(("double", "single")), default="double")
 @click.option("--host-alias", type=str, default=None)
 @click.option("--output-csv-file", type=str, default=None)
+@click.option("--output-csv-file-stencils", type=str, default=None, help="per-stencil device times (exec_info), one row per stencil")
+@click.option("--reference-file", type=str, default=None, help="golden NL outputs for --input-file (.h5 like data/reference_*.h5, or .npz)")
 @click.option("--input-file", type=str, default=None, help="input.h5 (default: tests/golden/input.h5 if present, else synthetic)")
 @click.option("--atol", type=float, default=None)
 @click.option("--rtol", type=float, default=None)
-def main(backend, enable_checks, enable_validation, num_cols, num_runs, precision, host_alias, output_csv_file, input_file,
-         atol, rtol):
+def main(backend, enable_checks, enable_validation, num_cols, num_runs, precision, host_alias, output_csv_file,
+         output_csv_file_stencils, reference_file, input_file, atol, rtol):
     rtol = rtol if rtol is not None else (1e-12 if precision == "double" else 1e-5)
     config = (DEFAULT_CONFIG.with_precision(precision).with_backend(backend).with_checks(enable_checks)
-              .with_validation(enable_validation, atol if atol is not None else 0.0, rtol).with_num_cols(num_cols or 100)
+              .with_validation(enable_validation, atol if atol is not None else 0.0, rtol).with_num_cols(num_cols or 0)
               .with_num_runs(num_runs))
     if input_file:
         config.input_file = input_file
+    if reference_file:
+        config.reference_file = reference_file
     config.gt4py_config.exec_info = {}
     io_config = DEFAULT_IO_CONFIG.with_output_csv_file(output_csv_file).with_host_name(host_alias)
-    core(config, io_config)
+    config = core(config, io_config)
+    if output_csv_file_stencils is not None:  # reference drivers/run_nonlinear.py:221-232
+        write_stencils_performance_to_csv(output_csv_file_stencils, io_config.host_name, config.precision,
+                                          "nl-" + config.gt4py_config.backend, config.num_cols, config.num_threads,
+                                          config.num_runs, config.gt4py_config.exec_info, key_patterns=["cloudsc", "saturation"])
 
 
 if __name__ == "__main__":

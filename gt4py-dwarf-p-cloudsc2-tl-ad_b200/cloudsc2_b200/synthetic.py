@@ -152,3 +152,68 @@ def tile(block: Dict[str, np.ndarray], ncol: int) -> Dict[str, np.ndarray]:
         reps = -(-ncol // arr.shape[1])
         out[name] = np.ascontiguousarray(np.tile(arr, (1, reps))[:, :ncol])
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# `input.h5` / `reference_*.h5` look-alikes (the reference's own data/input.h5 is not shipped)
+# ------------------------------------------------------------------------------------------
+def input_h5_datasets(block: Dict[str, np.ndarray], params: Dict[str, object], timestep_s: float = 3600.0,
+                      dtype=np.float64) -> Dict[str, np.ndarray]:
+    """The datasets `setup.get_state` (reference setup.py:48-65) and `iox.HDF5Operator` (iox.py:212-244) read, under the
+    reference's names: 2-D fields `(K, IJ)` (full-level fields with KLEV rows, PAPH with KLEV + 1), the 5-species arrays
+    `PCLV` / `TENDENCY_CML_CLD` `(5, K, IJ)` (index 0 = liquid, 1 = ice), `KLON`, `KLEV`, `PTSPHY`, and every scalar of the
+    parameter models (prefix `YRECLDP_` / `YREPHLI_` where the reference uses one)."""
+    nz = block["f_ap"].shape[0] - 1
+    klon = block["f_ap"].shape[1]
+    full = lambda a: np.ascontiguousarray(a[:nz].astype(dtype))  # noqa: E731
+    d: Dict[str, np.ndarray] = {
+        "KLON": np.array([klon], dtype=np.int32), "KLEV": np.array([nz], dtype=np.int32),
+        "PTSPHY": np.array([timestep_s], dtype=dtype),
+        "PA": np.zeros((nz, klon), dtype=dtype), "PAP": full(block["f_ap"]), "PAPH": block["f_aph"].astype(dtype),
+        "PLU": full(block["f_lu"]), "PLUDE": full(block["f_lude"]), "PMFD": full(block["f_mfd"]), "PMFU": full(block["f_mfu"]),
+        "PQ": full(block["f_q"]), "PSUPSAT": full(block["f_supsat"]), "PT": full(block["f_t"]),
+        "TENDENCY_CML_Q": full(block["f_tnd_cml_q"]), "TENDENCY_CML_T": full(block["f_tnd_cml_t"]),
+    }
+    clv = np.zeros((5, nz, klon), dtype=dtype)
+    clv[0], clv[1] = full(block["f_ql"]), full(block["f_qi"])
+    cld = np.zeros((5, nz, klon), dtype=dtype)
+    cld[0], cld[1] = full(block["f_tnd_cml_ql"]), full(block["f_tnd_cml_qi"])
+    d["PCLV"], d["TENDENCY_CML_CLD"] = clv, cld
+    prefixes = {"yrecldp": "YRECLDP_", "yrephli": "YREPHLI_"}
+    for group, model in params.items():
+        for name, value in model.dict().items():
+            key = prefixes.get(group, "") + name
+            if isinstance(value, bool):
+                d[key] = np.array([int(value)], dtype=np.int32)
+            elif isinstance(value, int):
+                d[key] = np.array([value], dtype=np.int32)
+            else:
+                d[key] = np.array([value], dtype=np.float64)
+    return d
+
+
+def write_input_h5(filename: str, block: str = "base", params: Dict[str, object] = None, timestep_s: float = 3600.0,
+                   seed: int = 0, dtype=np.float64) -> None:
+    from . import h5lite, iox
+
+    blk = base_block(seed=seed) if block == "base" else cold_block(seed=seed + 1)
+    h5lite.write_file(filename, input_h5_datasets(blk, params or iox.ifs_defaults(), timestep_s, dtype))
+
+
+def write_reference_h5(filename: str, tendencies: Dict[str, np.ndarray], diagnostics: Dict[str, np.ndarray]) -> None:
+    """NL outputs under the dataset names of the reference's golden files data/reference_*.h5 (nonlinear/reference.py:28-55):
+    full-level fields with KLEV rows, fluxes with KLEV + 1, `TENDENCY_LOC_CLD` `(5, K, IJ)`."""
+    from . import h5lite
+
+    nz = tendencies["f_t"].shape[0] - 1
+    klon = tendencies["f_t"].shape[1]
+    dt = tendencies["f_t"].dtype
+    cld = np.zeros((5, nz, klon), dtype=dt)
+    cld[0], cld[1] = tendencies["f_ql"][:nz], tendencies["f_qi"][:nz]
+    h5lite.write_file(filename, {
+        "KLON": np.array([klon], dtype=np.int32), "KLEV": np.array([nz], dtype=np.int32),
+        "PCLC": diagnostics["f_clc"][:nz], "PCOVPTOT": diagnostics["f_covptot"][:nz],
+        "PFHPSL": diagnostics["f_fhpsl"], "PFHPSN": diagnostics["f_fhpsn"], "PFPLSL": diagnostics["f_fplsl"],
+        "PFPLSN": diagnostics["f_fplsn"], "TENDENCY_LOC_CLD": cld, "TENDENCY_LOC_Q": tendencies["f_q"][:nz],
+        "TENDENCY_LOC_T": tendencies["f_t"][:nz],
+    })

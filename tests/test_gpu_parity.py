@@ -322,6 +322,42 @@ def test_drivers_run_end_to_end(tmp_path):
     assert res.returncode == 1 and "The symmetry test failed." in res.stdout and "AD branch predicates: 'reference'" in res.stdout
 
 
+def test_nonlinear_driver_from_input_file_with_golden_validation(tmp_path):
+    """BASELINE config 1 in form: `run_nonlinear --input-file input.h5` validated against a golden file in the reference's
+    HDF5 layout -- with an input.h5 look-alike (the reference's own is not shipped) whose golden outputs come from the
+    oracle; --num-cols > KLON tiles the columns (i mod KLON); per-stencil times go to --output-csv-file-stencils."""
+    import subprocess
+    import sys
+
+    from cloudsc2_b200 import synthetic
+
+    inp, ref, csv_s = str(tmp_path / "input.h5"), str(tmp_path / "reference_double.h5"), str(tmp_path / "stencils.csv")
+    synthetic.write_input_h5(inp, block="base")
+    P = H.externals()
+    s = H.with_diagnostics(H.make_state("base"), P)
+    tn, dg = H.onp.cloudsc2_nl(s, H.DT, P)
+    synthetic.write_reference_h5(ref, tn, dg)
+    for extra in ([], ["--num-cols", "250"]):
+        res = subprocess.run([sys.executable, "-m", "drivers.run_nonlinear", "--input-file", inp, "--reference-file", ref,
+                              "--num-runs", "3", "--output-csv-file-stencils", csv_s, *extra],
+                             cwd=H.ROOT, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        assert "validation passed" in res.stdout and "golden.f_t" in res.stdout and "FAIL" not in res.stdout
+        assert ("250 columns" if extra else "100 columns") in res.stdout
+    rows = open(csv_s).read().splitlines()
+    assert rows[0].startswith("date,host,precision,variant,num_cols") and len(rows) == 1 + 2 * 2
+    assert sum("cloudsc2_nl" in r for r in rows) == 2 and sum("saturation" in r for r in rows) == 2
+    # and the state loader on the device equals the synthetic state it was written from
+    g = gh()
+    cfg, grid, st = g.make_grid_state("base", np.float64, 250)
+    from cloudsc2_b200 import setup
+
+    st2 = setup.get_state(setup.HDF5GridOperator(inp, grid, gt4py_config=cfg))
+    for name in ("f_ap", "f_aph", "f_t", "f_q", "f_ql", "f_qi", "f_lu", "f_lude", "f_mfu", "f_mfd", "f_supsat", "f_tnd_cml_t",
+                 "f_tnd_cml_q", "f_tnd_cml_ql", "f_tnd_cml_qi"):
+        assert torch.equal(st2[name].buffer, st[name].buffer), name
+
+
 def test_multi_gpu_sharded_taylor_and_symmetry():
     """N>1 on real GPUs (NCCL): sharded Taylor / symmetry equal the single-GPU run (tests/dist_gpu_worker.py)."""
     import subprocess
