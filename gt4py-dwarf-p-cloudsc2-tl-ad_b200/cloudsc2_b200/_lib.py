@@ -86,6 +86,7 @@ SIGNATURES = {
     "cs2_last_error": (C.c_char_p, []),
     "cs2_device_count": (C.c_int, []),
     "cs2_dfma_rate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "cs2_dfma_rate_regs": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cs2_level_tables_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "cs2_level_tables_build": (C.c_int, [C.POINTER(Params), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs2_saturation": (C.c_int, [C.POINTER(Dims), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

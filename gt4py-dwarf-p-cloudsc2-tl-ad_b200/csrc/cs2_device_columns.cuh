@@ -442,37 +442,37 @@ inline Streams<R, NS + (EVAP ? 2 : 0)> ad_streams(const NLFields<R>& f, const AD
   return o;
 }
 
-// NORM: also the symmetry test's second inner product, norm2[i] = SUM_k SUM_fields (fac * input) * (adjoint output) of the
-// column (adjoint/validation.py:183-215; the increments are StateIncrement's: products rounded on their own, supsat_i = 0
-// with ignore_supsat), accumulated in fp64 from the values as stored.
+// State a backward sweep carries from level k+1 to level k (and, in the level-chunked kernel, from the warp that did
+// the chunk below to the warp that does the next one).
+template <class R>
+struct AdCarry {
+  R a_rfl, a_sfl;   // adjoint of the fluxes entering the level below
+  R a_dp_below;     // a_dp of level k+1
+  R a_cov, a_aph_s; // evaporation branch: adjoint of the overlap carry / of the surface pressure
+  R aph1;           // aph[k+1]
+  double n2;        // NORM: running second inner product
+};
+
+// Levels k_hi ... k_lo (descending) of the backward sweep of one column; the inputs of level k_hi must already have been
+// issued into the ring (ring_issue at offset k_hi * S + i).
 template <class R, int BLOCK, int NS, bool EVAP = false, bool NORM = false>
-__device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
-                                                  const ADOut<R>& a, const Streams<R, NS + (EVAP ? 2 : 0)>& in_s,
-                                                  Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, const int32_t* jsel_in,
-                                                  uint32_t S, int nlev, uint32_t i, bool valid, R fac = R(0),
-                                                  bool ignore_supsat = false, double* norm2 = nullptr,
-                                                  R (*keep)[BLOCK] = nullptr, const ADSeeds<R>* zero_seeds = nullptr) {
+__device__ __forceinline__ void dev_ad_bwd_span(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                                const ADOut<R>& a, const Streams<R, NS + (EVAP ? 2 : 0)>& in_s,
+                                                Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, int jsel, R aph_s, uint32_t S,
+                                                int nlev, uint32_t i, bool valid, int k_hi, int k_lo, AdCarry<R>& cy, R fac,
+                                                bool ignore_supsat, R (*keep)[BLOCK], const ADSeeds<R>* zero_seeds) {
   constexpr bool CKPT = NS > B_N;
-  double n2 = 0.0;
   using C = Cfg<EVAP, true>;
   const bool ad_ref = !p.ad_tl_predicates;
-  ring_issue(ring, in_s, uint32_t(nlev - 1) * S + i);
-  const int jsel = jsel_in[i];
   const int ncand = tab.nw + 1;
-  const R aph_s = f.aph[uint32_t(nlev) * S + i];
   const int t = threadIdx.x;
-
-  R a_rfl = R(0), a_sfl = R(0);  // adjoint of the fluxes entering the level below
-  R a_dp_below = R(0);           // a_dp of level k+1
-  R a_cov = R(0), a_aph_s = R(0);  // evaporation branch: adjoint of the overlap carry / of the surface pressure
-  R aph1 = aph_s;
-  for (int k = nlev - 1; k >= 0; --k) {
+  for (int k = k_hi; k >= k_lo; --k) {
     const uint32_t off = uint32_t(k) * S + i;
     cp_async_wait_all();
     LevelIn<R> in;
     ring_read_level(ring, 0, R(0), in);
     in.aph0 = in.aph1;  // stream I_APH1 carries aph[k] in this sweep
-    in.aph1 = aph1;
+    in.aph1 = cy.aph1;
     if constexpr (NORM) {
       // the inner product needs every input again after level_ad: park them in shared memory instead of keeping 16 more
       // doubles live through the level (the backward kernel has no registers to spare)
@@ -492,15 +492,15 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     so.clc = ring.v[B_S_CLC][t];
     so.covptot = EVAP ? ring.v[NS + 1][t] : R(0);
     // flux seeds at half level k+1 with the enthalpy-flux seeds folded in (AD :479-484,500-501)
-    R a_rfln = a_rfl + (ring.v[B_S_FPLSL][t] - ring.v[B_S_FHPSL][t] * p.RLVTT);
-    R a_sfln = a_sfl + (ring.v[B_S_FPLSN][t] - ring.v[B_S_FHPSN][t] * p.RLSTT);
+    R a_rfln = cy.a_rfl + (ring.v[B_S_FPLSL][t] - ring.v[B_S_FHPSL][t] * p.RLVTT);
+    R a_sfln = cy.a_sfl + (ring.v[B_S_FPLSN][t] - ring.v[B_S_FHPSN][t] * p.RLSTT);
 
     Trans<R, CKPT ? 2 : 0> x;
     if constexpr (CKPT) {
 #pragma unroll
       for (int n = 0; n < CK_N; ++n) x.v[n] = ring.v[B_N + n][t];
     }
-    if (k > 0) ring_issue(ring, in_s, off - S);
+    if (k > k_lo) ring_issue(ring, in_s, off - S);
     if (zero_seeds && valid && k + CS2_AD_ZERO_LAG < nlev) {  // seeds of a level consumed CS2_AD_ZERO_LAG iterations ago
       const ADSeeds<R>& z = *zero_seeds;
       const uint32_t zo = off + uint32_t(CS2_AD_ZERO_LAG) * S;
@@ -512,9 +512,9 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
     Traj<R> tr;
     level_fwd<R, C, true>(p, in, tab.scalm[k], tab.crh2[k * ncand + jsel], k < nlev - 1, aph_s, ad_ref, c, o, tr, x);
     LevelIn<R> ad;
-    level_ad<R, C>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad, aph_s, &a_cov, &a_aph_s);
-    a_rfl = a_rfln;
-    a_sfl = a_sfln;
+    level_ad<R, C>(p, in, tr, so, ad_ref, a_rfln, a_sfln, ad, aph_s, &cy.a_cov, &cy.a_aph_s);
+    cy.a_rfl = a_rfln;
+    cy.a_sfl = a_sfln;
 
     if (valid) {
       const uint32_t offn = off + S;
@@ -526,49 +526,71 @@ __device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const L
       a.ap[off] = ad.ap;         a.lude[off] = ad.lude;
       a.mfu[off] = ad.mfu;       a.mfd[off] = ad.mfd;
       // staggered fields (AD :969-986): aph_i[k+1] = a_dp(k) - a_dp(k+1); lu_i[k+1] = adjoint of lu[k+1]
-      a.aph[offn] = ad.aph1 - a_dp_below;
+      a.aph[offn] = ad.aph1 - cy.a_dp_below;
       a.lu[offn] = ad.lu1;
     }
     if constexpr (NORM) {
       asm volatile("" ::: "memory");
       auto pr = [fac](R x, R adj) { return double(mul_rn(fac, x)) * double(adj); };
-      n2 += pr(keep[0][t], ad.t) + pr(keep[1][t], ad.q) + pr(keep[2][t], ad.ql) + pr(keep[3][t], ad.qi) +
-            pr(keep[4][t], ad.qsat) + pr(keep[5][t], ad.ap) + pr(keep[6][t], ad.lude) + pr(keep[7][t], ad.mfu) +
-            pr(keep[8][t], ad.mfd) + pr(keep[9][t], ad.tnd_t) + pr(keep[10][t], ad.tnd_q) + pr(keep[11][t], ad.tnd_ql) +
-            pr(keep[12][t], ad.tnd_qi) + pr(keep[13][t], R(ad.aph1 - a_dp_below)) + pr(keep[14][t], ad.lu1);
-      if (!ignore_supsat) n2 += pr(keep[15][t], ad.supsat);
+      cy.n2 += pr(keep[0][t], ad.t) + pr(keep[1][t], ad.q) + pr(keep[2][t], ad.ql) + pr(keep[3][t], ad.qi) +
+               pr(keep[4][t], ad.qsat) + pr(keep[5][t], ad.ap) + pr(keep[6][t], ad.lude) + pr(keep[7][t], ad.mfu) +
+               pr(keep[8][t], ad.mfd) + pr(keep[9][t], ad.tnd_t) + pr(keep[10][t], ad.tnd_q) + pr(keep[11][t], ad.tnd_ql) +
+               pr(keep[12][t], ad.tnd_qi) + pr(keep[13][t], R(ad.aph1 - cy.a_dp_below)) + pr(keep[14][t], ad.lu1);
+      if (!ignore_supsat) cy.n2 += pr(keep[15][t], ad.supsat);
     }
-    a_dp_below = ad.aph1;
-    aph1 = in.aph0;
+    cy.a_dp_below = ad.aph1;
+    cy.aph1 = in.aph0;
   }
-  if (valid) {
-    a.aph[i] = -a_dp_below;
-    a.lu[i] = R(0);
-    if (EVAP) a.aph[uint32_t(nlev) * S + i] += a_aph_s;  // adjoint of the surface pressure (AD :974-975); own earlier store
-    if constexpr (NORM) {
-      n2 += double(mul_rn(fac, aph1)) * double(R(-a_dp_below));  // half level 0 (aph1 holds aph[0] after the loop)
-      norm2[i] = n2;
+}
+
+// What the thread that reaches the top of a column does after its last level (k = 0).
+template <class R, bool EVAP, bool NORM>
+__device__ __forceinline__ void dev_ad_bwd_finish(const ADOut<R>& a, uint32_t S, int nlev, uint32_t i, const AdCarry<R>& cy,
+                                                  R fac, double* norm2, const ADSeeds<R>* zero_seeds) {
+  a.aph[i] = -cy.a_dp_below;
+  a.lu[i] = R(0);
+  if (EVAP) a.aph[uint32_t(nlev) * S + i] += cy.a_aph_s;  // adjoint of the surface pressure (AD :974-975); own earlier store
+  if constexpr (NORM) {
+    norm2[i] = cy.n2 + double(mul_rn(fac, cy.aph1)) * double(R(-cy.a_dp_below));  // half level 0 (aph1 holds aph[0] here)
+  }
+  // The reference consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).  A column's
+  // seeds are read by its own thread(s) only, so the sweep resets them itself: inside the level loop the seeds of the level
+  // consumed CS2_AD_ZERO_LAG iterations earlier (plain stores off the dependent chain, spread over the sweep), here the
+  // last few levels.  Measured at 65 536 columns: 1.29 ms with 10 cudaMemsetAsync after the kernel, 1.25 ms with one
+  // trailing burst of stores, 1.19 ms with the lagged in-loop stores (any lag from 1 to 16); zeroing a slot right after
+  // its own load, as the very first version did, serialises in L2 and was 4x slower (profiles/r1c_ad_bwd.md).
+  if (zero_seeds) {
+    const ADSeeds<R>& z = *zero_seeds;
+    const int ktail = nlev < CS2_AD_ZERO_LAG ? nlev : CS2_AD_ZERO_LAG;  // the levels the in-loop reset has not reached
+    for (int k = 0; k < ktail; ++k) {
+      const uint32_t off = uint32_t(k) * S + i;
+      z.tnd_t[off] = R(0); z.tnd_q[off] = R(0); z.tnd_ql[off] = R(0); z.tnd_qi[off] = R(0); z.clc[off] = R(0);
+      z.covptot[off] = R(0);
     }
-    // The reference consumes its seeds (adjoint/_stencils/cloudsc2.py:482-484,506-542,650,714,920,972-984).  A column's
-    // seeds are read by this thread only, so the thread resets them itself: inside the level loop the seeds of the level
-    // consumed CS2_AD_ZERO_LAG iterations earlier (plain stores off the dependent chain, spread over the sweep), here the
-    // last few levels.  Measured at 65 536 columns: 1.29 ms with 10 cudaMemsetAsync after the kernel, 1.25 ms with one
-    // trailing burst of stores, 1.19 ms with the lagged in-loop stores (any lag from 1 to 16); zeroing a slot right after
-    // its own load, as the very first version did, serialises in L2 and was 4x slower (profiles/r1c_ad_bwd.md).
-    if (zero_seeds) {
-      const ADSeeds<R>& z = *zero_seeds;
-      const int ktail = nlev < CS2_AD_ZERO_LAG ? nlev : CS2_AD_ZERO_LAG;  // the levels the in-loop reset has not reached
-      for (int k = 0; k < ktail; ++k) {
-        const uint32_t off = uint32_t(k) * S + i;
-        z.tnd_t[off] = R(0); z.tnd_q[off] = R(0); z.tnd_ql[off] = R(0); z.tnd_qi[off] = R(0); z.clc[off] = R(0);
-        z.covptot[off] = R(0);
-      }
-      for (int k = 0; k <= ktail; ++k) {  // half-level seeds: one more level
-        const uint32_t off = uint32_t(k) * S + i;
-        z.fhpsl[off] = R(0); z.fhpsn[off] = R(0); z.fplsl[off] = R(0); z.fplsn[off] = R(0);
-      }
+    for (int k = 0; k <= ktail; ++k) {  // half-level seeds: one more level
+      const uint32_t off = uint32_t(k) * S + i;
+      z.fhpsl[off] = R(0); z.fhpsn[off] = R(0); z.fplsl[off] = R(0); z.fplsn[off] = R(0);
     }
   }
+}
+
+// NORM: also the symmetry test's second inner product, norm2[i] = SUM_k SUM_fields (fac * input) * (adjoint output) of the
+// column (adjoint/validation.py:183-215; the increments are StateIncrement's: products rounded on their own, supsat_i = 0
+// with ignore_supsat), accumulated in fp64 from the values as stored.
+template <class R, int BLOCK, int NS, bool EVAP = false, bool NORM = false>
+__device__ __forceinline__ void dev_column_ad_bwd(const DevParams<R>& p, const LevelTables<R>& tab, const NLFields<R>& f,
+                                                  const ADOut<R>& a, const Streams<R, NS + (EVAP ? 2 : 0)>& in_s,
+                                                  Ring<R, NS + (EVAP ? 2 : 0), BLOCK>& ring, const int32_t* jsel_in,
+                                                  uint32_t S, int nlev, uint32_t i, bool valid, R fac = R(0),
+                                                  bool ignore_supsat = false, double* norm2 = nullptr,
+                                                  R (*keep)[BLOCK] = nullptr, const ADSeeds<R>* zero_seeds = nullptr) {
+  ring_issue(ring, in_s, uint32_t(nlev - 1) * S + i);
+  const int jsel = jsel_in[i];
+  const R aph_s = f.aph[uint32_t(nlev) * S + i];
+  AdCarry<R> cy{R(0), R(0), R(0), R(0), R(0), aph_s, 0.0};
+  dev_ad_bwd_span<R, BLOCK, NS, EVAP, NORM>(p, tab, f, a, in_s, ring, jsel, aph_s, S, nlev, i, valid, nlev - 1, 0, cy, fac,
+                                            ignore_supsat, keep, zero_seeds);
+  if (valid) dev_ad_bwd_finish<R, EVAP, NORM>(a, S, nlev, i, cy, fac, norm2, zero_seeds);
 }
 
 }  // namespace cs2

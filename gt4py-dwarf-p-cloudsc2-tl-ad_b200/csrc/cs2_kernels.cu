@@ -17,6 +17,7 @@
 
 #include "cs2_device_columns.cuh"
 #ifdef CS2_EXPERIMENTS  // measured-and-rejected kernel variants (profiles/README.md); not in the shipped library
+#include "experiments/cs2_ad_chunked.cuh"
 #include "experiments/cs2_bulk_columns.cuh"
 #include "experiments/cs2_pipe_columns.cuh"
 #include "experiments/cs2_split_columns.cuh"
@@ -303,6 +304,23 @@ ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
                                                         ignore_supsat != 0, norm2, keep, zero_seeds ? &seeds : nullptr);
 }
 
+#ifdef CS2_EXPERIMENTS
+// level-chunked backward sweep with persistent warps (default flags, recompute mode): see dev_ad_bwd_chunked
+template <class R>
+__global__ void __maxnreg__(CS2_AD_MAXNREG)
+ad_bwd_chunked_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
+                      const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
+                      const __grid_constant__ cs2::Streams<R, cs2::B_N> in_s, const int32_t* __restrict__ jsel, int64_t ncol,
+                      int64_t S, int nlev, const __grid_constant__ cs2::ADSeeds<R> seeds, int zero_seeds, int nchunk,
+                      int chunk_levels, unsigned* ticket, R* carry) {
+  __shared__ cs2::Ring<R, cs2::B_N, kWideBlock> ring;
+  const cs2::LevelTables<R> tab = cs2::view_tables<R>(tables);
+  cs2::dev_ad_bwd_chunked<R, kWideBlock>(p, tab, f, a, in_s, ring, jsel, uint32_t(S), nlev, uint32_t(ncol), nchunk, chunk_levels,
+                                         ticket, carry, zero_seeds ? &seeds : nullptr);
+}
+
+#endif  // CS2_EXPERIMENTS
+
 // ---- FP64 pipe micro-benchmark (the roofline's second axis: MEASURED_PEAKS.json has no FP64 entry) -----------
 __global__ void __launch_bounds__(256) dfma_rate_kernel(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -311,6 +329,32 @@ __global__ void __launch_bounds__(256) dfma_rate_kernel(double* out, int iters, 
     x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
   }
   out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// Same with all three operands in REGISTERS that differ per chain (what the column kernels' DFMAs look like: products and
+// sums of per-column values), and with the mix of the physics: a dependent pair DMUL -> DFMA per chain.  MODE 1: x = fma(x, y, z);
+// MODE 2: x = fma(x * y, z, w).
+template <int MODE>
+__global__ void __launch_bounds__(256) dfma_rate_regs_kernel(double* out, int iters, const double* __restrict__ seed) {
+  const int t = threadIdx.x;
+  double x[8], y[8], z[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    x[n] = seed[(t + n) & 255];
+    y[n] = 0.999999 + 1e-9 * seed[(t + 3 * n + 1) & 255];
+    z[n] = 1e-6 * seed[(t + 5 * n + 2) & 255];
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (MODE == 1) x[n] = fma(x[n], y[n], z[n]);
+      else x[n] = fma(x[n] * y[n], y[(n + 1) & 7], z[n]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) s += x[n];
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = s;
 }
 
 // ---- reductions -----------------------------------------------------------------------
@@ -711,12 +755,75 @@ cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 }  // namespace
 
 namespace {
+// AD workspace: [jsel: int32 per column] [checkpoint planes | overlap-carry plane]; with -DCS2_EXPERIMENTS also [chunk ticket
+// counter] [chunk hand-over slots: 3 values per column and chunk boundary, up to kMaxAdChunks - 1 boundaries]
+constexpr int kMaxAdChunks = 8;
+struct AdWorkspace {
+  size_t off_extra, off_sync, sync_bytes, off_carry, total;
+};
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+inline AdWorkspace ad_workspace(const cs2_dims* d, const cs2_params* P, int mode) {
+  AdWorkspace w;
+  const size_t es = d->dtype == CS2_F32 ? 4 : 8;
+  const size_t plane = size_t(d->nlev) * size_t(d->ncol_stride) * es;
+  w.off_extra = align256(size_t(d->ncol_stride) * sizeof(int32_t));
+  size_t extra = 0;
+  if (P && (P->LEVAPLS2 || P->LDRAIN1D)) extra = plane;        // evaporation branch: overlap carry per (level, column)
+  else if (mode == CS2_AD_CHECKPOINT) extra = size_t(cs2::CK_N) * plane;  // CK_N transcendental results per (level, column)
+  w.off_sync = align256(w.off_extra + extra);
+#ifdef CS2_EXPERIMENTS
+  w.sync_bytes = 256;
+  w.off_carry = w.off_sync + w.sync_bytes;
+  w.total = align256(w.off_carry + size_t(kMaxAdChunks - 1) * 3 * size_t(d->ncol_stride) * es);
+#else
+  w.sync_bytes = 0;
+  w.off_carry = w.off_sync;
+  w.total = w.off_sync;
+#endif
+  return w;
+}
+
+#ifdef CS2_EXPERIMENTS
+// How many level chunks the backward sweep is cut into (0: whole-column sweeps).  Whole columns need ceil(warps / slots)
+// rounds, chunked ones ceil(warps * C / slots) / C: worth it when a mostly empty last round would cost a full one.
+template <class R>
+int ad_bwd_chunks(const cs2_dims* d, int* slots_cta_out) {
+  static const int forced = []() { const char* e = std::getenv("CS2_AD_CHUNKS"); return e ? std::atoi(e) : -1; }();
+  int dev = 0, nsm = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ad_bwd_chunked_kernel<R>, kWideBlock, 0) != cudaSuccess ||
+      nsm < 1 || per_sm < 1) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  const int64_t slots = int64_t(nsm) * per_sm;  // CTAs resident at once
+  *slots_cta_out = int(slots);
+  if (forced >= 0) return (forced <= 1 || forced > kMaxAdChunks || d->nlev < 2 * forced) ? 0 : forced;
+  return 0;  // measured: no gain (the sweep is FP64-issue-bound, not round-bound), so never chosen automatically
+  const int64_t ctas = (d->ncol + kWideBlock - 1) / kWideBlock;
+  const double rounds = double((ctas + slots - 1) / slots);
+  int best = 0;
+  double best_rounds = 0.93 * rounds;  // must save at least 7 % to pay for the hand-overs
+  for (int c : {4, 8}) {
+    if (d->nlev < 4 * c) continue;
+    const double r = double((ctas * c + slots - 1) / slots) / c;
+    if (r < best_rounds) {
+      best_rounds = r;
+      best = c;
+    }
+  }
+  return best;
+}
+
+#endif  // CS2_EXPERIMENTS
+
 template <class R>
 int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tables, const cs2_nl_fields* traj,
               const cs2_ad_seeds* seeds, const cs2_ad_outputs* adj, void* ws, int mode, cudaStream_t st,
               double factor = 0.0, int32_t ignore_supsat = 0, double* norm2 = nullptr) {
   int32_t* jsel = static_cast<int32_t*>(ws);
-  R* const after_jsel = reinterpret_cast<R*>(static_cast<char*>(ws) + ((size_t(d->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255)));
+  const AdWorkspace wsl = ad_workspace(d, P, mode);
+  R* const after_jsel = reinterpret_cast<R*>(static_cast<char*>(ws) + wsl.off_extra);
   // evaporation branch (LEVAPLS2 / LDRAIN1D, non-default): always the recompute sweep, plus the overlap carry per level
   const bool evap = P->LEVAPLS2 || P->LDRAIN1D;
   R* ck = (!evap && mode == CS2_AD_CHECKPOINT) ? after_jsel : nullptr;
@@ -750,6 +857,25 @@ int launch_ad(const cs2_dims* d, const cs2_params* P, double dt, const void* tab
                                                           cs2::ad_streams<R, NS, E>(nf, s, d->ncol_stride, d->nlev, CK, COV), \
                                                           jsel, d->ncol, d->ncol_stride, d->nlev, R(factor), ignore_supsat,  \
                                                           norm2, s, zero_in_kernel)
+#ifdef CS2_EXPERIMENTS  // level-chunked sweep with persistent warps: CS2_AD_CHUNKS=C (profiles/r2n_ad_chunked.md)
+  int slots_cta = 0;
+  int nchunk = (!evap && !ck && !norm2) ? ad_bwd_chunks<R>(d, &slots_cta) : 0;
+  if (nchunk > 1) {  // level-chunked sweep with persistent warps (see dev_ad_bwd_chunked)
+    unsigned* ticket = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + wsl.off_sync);
+    R* carry = reinterpret_cast<R*>(static_cast<char*>(ws) + wsl.off_carry);
+    const int chunk_levels = (d->nlev + nchunk - 1) / nchunk;
+    nchunk = (d->nlev + chunk_levels - 1) / chunk_levels;  // no empty last chunk
+    if (int rc = check_cuda(cudaMemsetAsync(ticket, 0, wsl.sync_bytes, st), "cloudsc2_ad chunk ticket reset")) return rc;
+    // hand-over slots: all-ones = "not written yet"
+    if (int rc = check_cuda(cudaMemsetAsync(carry, 0xFF, size_t(nchunk - 1) * 3 * size_t(d->ncol_stride) * sizeof(R), st),
+                            "cloudsc2_ad chunk hand-over reset"))
+      return rc;
+    const int64_t want = ((d->ncol + 31) / 32 + 1) / 2;  // never more CTAs than pairs of column groups
+    const unsigned pgrid = (unsigned)(want < slots_cta ? want : slots_cta);
+    ad_bwd_chunked_kernel<R><<<pgrid, kWideBlock, 0, st>>>(dp, tables, nf, a, cs2::ad_streams<R, cs2::B_N, false>(nf, s, d->ncol_stride, d->nlev, nullptr, nullptr),
+                                                          jsel, d->ncol, d->ncol_stride, d->nlev, s, zero_in_kernel, nchunk, chunk_levels, ticket, carry);
+  } else
+#endif
   if (evap) CS2_LAUNCH_BWD(cs2::B_N, true, false, nullptr, cov);
   else if (ck && norm2) CS2_LAUNCH_BWD(cs2::B_NCK, false, true, ck, nullptr);
   else if (norm2) CS2_LAUNCH_BWD(cs2::B_N, false, true, nullptr, nullptr);
@@ -819,6 +945,15 @@ int cs2_dfma_rate(double* scratch_dev, int32_t blocks, int32_t iters, void* stre
   if (blocks < 1 || iters < 1) return fail(CS2_ERR_BAD_DIMS, "dfma_rate: blocks and iters must be positive");
   dfma_rate_kernel<<<blocks, 256, 0, as_stream(stream)>>>(scratch_dev, iters, 0.999999, 1e-6);
   return check_cuda(cudaGetLastError(), "dfma_rate launch");
+}
+
+int cs2_dfma_rate_regs(double* scratch_dev, int32_t blocks, int32_t iters, int32_t mode, void* stream) {
+  if (!scratch_dev) return fail(CS2_ERR_NULL_POINTER, "dfma_rate_regs: scratch is NULL");
+  if (blocks < 2 || iters < 1 || (mode != 1 && mode != 2)) return fail(CS2_ERR_BAD_DIMS, "dfma_rate_regs: bad blocks / iters / mode");
+  // the first 256 doubles of the scratch buffer are the operand seeds (the caller fills them), results go behind them
+  if (mode == 1) dfma_rate_regs_kernel<1><<<blocks - 1, 256, 0, as_stream(stream)>>>(scratch_dev + 256, iters, scratch_dev);
+  else dfma_rate_regs_kernel<2><<<blocks - 1, 256, 0, as_stream(stream)>>>(scratch_dev + 256, iters, scratch_dev);
+  return check_cuda(cudaGetLastError(), "dfma_rate_regs launch");
 }
 
 int cs2_saturation(const cs2_dims* dims, const cs2_params* params, const void* in_ap, const void* in_t,
@@ -908,13 +1043,7 @@ int cs2_tl_increment(const cs2_dims* dims, const cs2_params* params, double dt, 
 
 size_t cs2_ad_workspace_bytes(const cs2_dims* dims, const cs2_params* params, int32_t mode) {
   if (!dims || dims->ncol_stride <= 0) return 0;
-  size_t bytes = (size_t(dims->ncol_stride) * sizeof(int32_t) + 255) & ~size_t(255);  // tropopause candidate per column
-  const size_t plane = size_t(dims->nlev) * size_t(dims->ncol_stride) * (dims->dtype == CS2_F32 ? 4 : 8);
-  if (params && (params->LEVAPLS2 || params->LDRAIN1D))
-    bytes += plane;  // evaporation branch: overlap carry per (level, column); the sweep is always the recompute one
-  else if (mode == CS2_AD_CHECKPOINT)
-    bytes += size_t(cs2::CK_N) * plane;  // CK_N transcendental results per (level, column)
-  return (bytes + 255) & ~size_t(255);
+  return ad_workspace(dims, params, mode).total;
 }
 
 int cs2_ad(const cs2_dims* dims, const cs2_params* params, double dt, const void* level_tables_dev,

@@ -97,6 +97,11 @@ int cs2_device_count(void);
  * (>= blocks * 256 doubles).  Timed with CUDA events by bench.py to put the FP64-pipe peak of the
  * device next to the HBM peak (the roofline's second axis). */
 int cs2_dfma_rate(double* scratch_dev, int32_t blocks, int32_t iters, void* stream);
+/* Same measurement with every DFMA operand in a per-thread register (mode 1: x = fma(x, y, z); mode 2: the dependent pair
+ * x = fma(x * y, y', z)), i.e. the operand pattern of the column kernels instead of two uniform operands.  The first 256 doubles
+ * of `scratch_dev` are the operand seeds (caller-filled, O(1) values), (blocks - 1) * 256 results follow.
+ * flops per launch: mode 1: (blocks - 1) * 256 * 8 * iters * 2;  mode 2: ... * 3. */
+int cs2_dfma_rate_regs(double* scratch_dev, int32_t blocks, int32_t iters, int32_t mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Level tables.  Everything that depends on the level only -- `scalm = ZSCAL*max(eta-0.2,
