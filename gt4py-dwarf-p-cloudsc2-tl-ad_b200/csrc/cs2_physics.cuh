@@ -52,6 +52,7 @@ struct AdjStep {
   R rt;                 // 1 / (t - z4es)
   R foeew, qsc, cor, qs, z2s, rden, cond;
   bool clipped;         // foeew / ap > ZQMAX
+  R ct, cap;            // local Jacobian (adj_step_coef): cond_i = rden q_i + ct t_i + cap ap_i
 };
 
 // Trajectory of a level.  Everything is a plain local; members that a caller does not read
@@ -205,6 +206,24 @@ CS2_HD void saturation_points(const DevParams<R>& p, bool lphylin, const R (&ap)
   }
 }
 
+// Local Jacobian of one Newton step, formed from the trajectory alone (pre-accumulation):
+//   cond_i = rden q_i + ct t_i + cap ap_i
+// -- the statements of tangent_linear/_stencils/cuadjtqs.py:22-55 collected by input (with 1 + RETV qs = cor), whose
+// transpose is adjoint/_stencils/cuadjtqs.py:93-124.  The adjoint of the step is then
+//   a_cond = zal a_t - a_q;  a_q += rden a_cond;  a_t += ct a_cond;  a_ap += cap a_cond
+// i.e. four dependent FMAs on the backward sweep's critical path instead of a chain of a dozen products; the coefficients are
+// evaluated by the forward recomputation (adj_step<LIN>), off that path.  Measured: AD 1.180 -> 1.138 ms at 65 536 columns
+// together with the shared products in level_ad (profiles/r2q_ad_preaccumulation.md).
+template <class R>
+CS2_HD void adj_step_coef(const DevParams<R>& p, R rap, R r5, const AdjStep<R>& s, R& ct, R& cap) {
+  const R h = s.cond * s.z2s;
+  const R e = s.rden * (s.cor * s.cor) * (R(1) + h * (s.cor + p.RETV * s.qs));  // -d cond / d qsc
+  const R f = R(2) * s.rden * h * s.qs * s.cor * s.rt;                            // d cond / d t through z2s
+  const R fr = s.clipped ? R(0) : s.foeew * rap;
+  ct = f - e * (fr * r5 * (s.rt * s.rt));
+  cap = e * fr * rap;
+}
+
 // ---------------------------------------------------------------------------------------
 // saturation adjustment step (nonlinear/_stencils/cuadjtqs.py:22-35)
 // ---------------------------------------------------------------------------------------
@@ -212,6 +231,7 @@ CS2_HD void saturation_points(const DevParams<R>& p, bool lphylin, const R (&ap)
 // use an algebraically merged form with one reciprocal on the critical path instead of two in sequence.
 template <class R, bool LIN, class X>
 CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t, R& q, AdjStep<R>& s, X& x, int ck) {
+  s.ct = s.cap = R(0);
   s.t = t;
   s.q = q;
   s.rt = rcp(t - z4);
@@ -221,10 +241,16 @@ CS2_HD void adj_step(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, R& t
   s.qsc = s.clipped ? p.ZQMAX : qs1;
   s.z2s = z5 * s.rt * s.rt;
   if (LIN) {
-    s.cor = rcp(R(1) - p.RETV * s.qsc);
+    // the two reciprocals side by side (cor feeds rden in the literal form): rden = 1 / (1 + qsc cor^2 z2s) = a^2 / (a^2 + qsc z2s),
+    // a = 1 - RETV qsc = 1 / cor.  adj_step_fwd_tl (cs2_physics_tl.cuh) has the same statements: TL and AD trajectories stay
+    // bit-identical
+    const R a = R(1) - p.RETV * s.qsc;
+    s.cor = rcp(a);
+    const R a2 = a * a;
+    s.rden = a2 * rcp(a2 + s.qsc * s.z2s);
     s.qs = s.qsc * s.cor;
-    s.rden = rcp(R(1) + s.qs * s.cor * s.z2s);
     s.cond = (q - s.qs) * s.rden;
+    adj_step_coef(p, rap, z3 * (p.RTT - z4), s, s.ct, s.cap);
   } else {
     // cond = (q - qsc/a) / (1 + qsc z2s / a^2) = a (q a - qsc) / (a^2 + qsc z2s),  a = 1 - RETV qsc
     const R a = R(1) - p.RETV * s.qsc;
@@ -249,24 +275,6 @@ CS2_HD void adj_step_tl(const DevParams<R>& p, R rap, R ap_i, R z3, R z4, R z5, 
                    (s.q - s.qs) * (qs_i * s.cor * s.z2s + s.qs * cor_i * s.z2s + s.qs * s.cor * z2s_i) * s.rden * s.rden;
   t_i += zal * cond_i;
   q_i -= cond_i;
-}
-
-// transpose of adj_step_tl (adjoint/_stencils/cuadjtqs.py:93-124)
-template <class R>
-CS2_HD void adj_step_ad(const DevParams<R>& p, R rap, R z3, R z4, R z5, R zal, const AdjStep<R>& s, R& a_t,
-                        R& a_q, R& a_ap) {
-  const R a_cond = zal * a_t - a_q;
-  a_q += a_cond * s.rden;
-  const R w = s.cond * s.rden * a_cond;
-  R a_qs = -a_cond * s.rden - w * s.cor * s.z2s;
-  R a_cor = -w * s.qs * s.z2s;
-  const R a_z2s = -w * s.qs * s.cor;
-  a_t += R(-2) * z5 * s.rt * s.rt * s.rt * a_z2s;
-  a_cor += a_qs * s.qsc;
-  R a_qsc = a_qs * s.cor + p.RETV * s.cor * s.cor * a_cor;
-  if (s.clipped) a_qsc = R(0);
-  a_ap -= a_qsc * s.foeew * rap * rap;
-  a_t += a_qsc * rap * s.foeew * z3 * (p.RTT - z4) * s.rt * s.rt;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -312,7 +320,6 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   tr.rtw = rcp(t0 - p.R4LES);
   tr.rti = rcp(t0 - p.R4IES);
   tr.cold = t0 < p.RTT;
-  R esdp;
   if (C::TETENS) {
     if (tr.cold) {
       tr.tp1 = x.tp1(R(0.17) * (t0 - p.RLPTRC));
@@ -328,9 +335,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
       tr.rtm4 = tr.rtw;
     }
     tr.foeew = p.R2ES * x.exp(CK_FOEEW, tr.z3es * (t0 - p.RTT) * tr.rtm4);
-    const R esdp1 = tr.foeew * tr.rap;
-    tr.clip_esdp = esdp1 > p.ZQMAX;
-    esdp = tr.clip_esdp ? p.ZQMAX : esdp1;
+    tr.clip_esdp = tr.foeew * tr.rap > p.ZQMAX;  // esdp = min(foeew / ap, ZQMAX) binds
   } else {
     tr.tp1 = R(2);
     tr.fwat = foealfa(p, t0);
@@ -339,7 +344,6 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
     tr.z4es = p.R4LES;
     tr.rtm4 = tr.rtw;
     tr.clip_esdp = false;
-    esdp = tr.foeew * tr.rap;
   }
   tr.facw = p.R5LES * tr.rtw * tr.rtw;
   tr.faci = p.R5IES * tr.rti * tr.rti;
@@ -347,10 +351,7 @@ CS2_HD void level_fwd(const DevParams<R>& p, const LevelIn<R>& in, R scalm, R cr
   // cor = 1 / (1 - RETV esdp); with esdp = foeew / ap unclipped this is ap / (ap - RETV foeew) = ap * fac2,
   // and fac2 is needed by the subsidence term anyway: one reciprocal less per level
   tr.fac2 = rcp(in.ap - p.RETV * tr.foeew);
-  if (LIN)
-    tr.cor = rcp(one - p.RETV * esdp);
-  else
-    tr.cor = tr.clip_esdp ? p.cor_clip : in.ap * tr.fac2;
+  tr.cor = tr.clip_esdp ? p.cor_clip : in.ap * tr.fac2;
   tr.dqsdtemp = tr.fac * tr.cor * in.qsat;
   tr.corqs = one + p.cons3 * tr.dqsdtemp;
   tr.qlim = min_(tr.q0, in.qsat);
@@ -845,8 +846,16 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
 
   // ---- saturation adjustment (AD :594-598)
   R a_t = zero, a_ap = zero;
-  adj_step_ad(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, tr.sa, a_t, a_q, a_ap);
-  adj_step_ad(p, tr.rap, tr.z3c, tr.z4c, tr.z5c, tr.zalc, tr.sb, a_t, a_q, a_ap);
+  {
+    R a_cond = tr.zalc * a_t - a_q;  // second step
+    a_q += tr.sa.rden * a_cond;
+    a_t += tr.sa.ct * a_cond;
+    a_ap += tr.sa.cap * a_cond;
+    a_cond = tr.zalc * a_t - a_q;    // first step
+    a_q += tr.sb.rden * a_cond;
+    a_t += tr.sb.ct * a_cond;
+    a_ap += tr.sb.cap * a_cond;
+  }
 
   // ---- first-guess T and q (AD :600-633)
   a_q += a_qold;
@@ -1020,21 +1029,25 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
     R a_dqc = -a_qc3;
     if (p.lregcl) a_dqc *= R(0.1);
     a_qc2 = a_qc3;
-    a_dqsdz = p.dt * a_dqc * tr.mfsum * tr.fac4;
-    a_mf = p.dt * a_dqc * tr.dqsdz * tr.fac4;
-    a_rho = -a_dqc * tr.dqc * tr.fac4;
+    const R wd = a_dqc * tr.fac4, wdt = p.dt * wd;
+    a_dqsdz = wdt * tr.mfsum;
+    a_mf = wdt * tr.dqsdz;
+    a_rho = -(wd * tr.dqc);
   }
   const R a_dtdzmo = a_dqsdz * tr.dqsdtemp;
-  R a_dqsdtemp = a_dqsdz * tr.dtdzmo - tr.dtdzmo * a_dtdzmo * tr.ldcp * tr.fac3;
-  const R a_rodqsdp = -p.RG * (a_dqsdz + a_dtdzmo * tr.ldcp * tr.fac3);
-  a_ldcp += -a_dtdzmo * (p.RG * tr.rodqsdp + tr.dtdzmo * tr.dqsdtemp) * tr.fac3;
-  a_fwat += a_ldcp * (tr.lvdcp - tr.lsdcp);
+  const R gz = a_dtdzmo * tr.fac3, hz = gz * tr.ldcp;
+  R a_dqsdtemp = tr.dtdzmo * (a_dqsdz - hz);
+  const R a_rodqsdp = -p.RG * (a_dqsdz + hz);
+  a_ldcp -= gz * (p.RG * tr.rodqsdp + tr.dtdzmo * tr.dqsdtemp);
+  a_fwat -= a_ldcp * dlv;
   a_lvdcp += tr.fwat * a_ldcp;
   a_lsdcp += (one - tr.fwat) * a_ldcp;
-  a_rho -= a_rodqsdp * in.qsat * tr.fac2;
-  R a_qs = -a_rodqsdp * tr.rho * tr.fac2;
+  const R mq = a_rodqsdp * tr.fac2;
+  a_rho -= mq * in.qsat;
+  const R mr = mq * tr.rho;
+  R a_qs = -mr;
   if (C::EVAP) a_qs += a_qs_ev;
-  const R rq2 = a_rodqsdp * tr.rho * in.qsat * tr.fac2 * tr.fac2;
+  const R rq2 = mr * in.qsat * tr.fac2;
   a_ap += rq2 + a_rho * tr.fac1;
   R a_foeew = -p.RETV * rq2;
   a_t0 -= a_rho * tr.rho * (p.RD * tr.fac1);
@@ -1042,13 +1055,15 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
   // ---- convective component (AD :857-877)
   R a_lude = zero, a_lu1 = zero, a_qc1 = a_qc2;
   if (tr.lo1) {
-    a_lude = a_qc2 + (one - tr.clc) * tr.rlu1 * tr.ex * a_clc;
-    a_lu1 = -(one - tr.clc) * tr.lude * tr.rlu1 * tr.rlu1 * tr.ex * a_clc;
+    const R wc = (one - tr.clc) * tr.rlu1 * tr.ex * a_clc;
+    a_lude = a_qc2 + wc;
+    a_lu1 = -(wc * tr.lude * tr.rlu1);
     a_clc *= tr.ex;
   }
-  a_lude_in += p.dt * tr.gdp * a_lude;
-  a_gdp += p.dt * in.lude * a_lude;
-  a_dp -= p.RG * tr.rdp * tr.rdp * a_gdp;
+  const R dtl = p.dt * a_lude;
+  a_lude_in += dtl * tr.gdp;
+  a_gdp += dtl * in.lude;
+  a_dp -= tr.gdp * tr.rdp * a_gdp;  // gdp = RG / dp
 
   // ---- cloud fraction and condensate (AD :879-923)
   R a_qt = zero, a_qsat = zero, a_qcrit = zero;
@@ -1086,17 +1101,19 @@ CS2_HD void level_ad(const DevParams<R>& p, const LevelIn<R>& in, const Traj<R>&
 
   // ---- dqs/dT correction factor (AD :940-967)
   if (C::EVAP) a_dqsdtemp += p.cons3 * a_corqs;
+  const R xq = a_dqsdtemp * in.qsat;
   a_qs += tr.fac * tr.cor * a_dqsdtemp;
-  const R a_cor = tr.fac * in.qsat * a_dqsdtemp;
-  const R a_fac = tr.cor * in.qsat * a_dqsdtemp;
-  R a_esdp = p.RETV * a_cor * tr.cor * tr.cor;
+  const R a_cor = tr.fac * xq;
+  const R a_fac = tr.cor * xq;
+  R a_esdp = p.RETV * (tr.cor * tr.cor) * a_cor;
   a_fwat += (tr.facw - tr.faci) * a_fac;
-  a_t0 -= R(2) * (p.R5IES * (one - tr.fwat) * a_fac * tr.rti * tr.rti * tr.rti +
-                  p.R5LES * tr.fwat * a_fac * tr.rtw * tr.rtw * tr.rtw);
+  // facw = R5LES rtw^2, faci = R5IES rti^2 (trajectory): their temperature derivatives are -2 facw rtw, -2 faci rti
+  a_t0 -= R(2) * a_fac * ((one - tr.fwat) * tr.faci * tr.rti + tr.fwat * tr.facw * tr.rtw);
   if (tr.clip_esdp) a_esdp = zero;
-  a_foeew += a_esdp * tr.rap;
-  a_ap -= a_esdp * tr.foeew * tr.rap * tr.rap;
-  a_t0 += tr.z3es * (p.RTT - tr.z4es) * a_foeew * tr.foeew * tr.rtm4 * tr.rtm4;
+  const R ue = a_esdp * tr.rap;
+  a_foeew += ue;
+  a_ap -= ue * tr.foeew * tr.rap;
+  a_t0 += tr.z3es * (p.RTT - tr.z4es) * (tr.rtm4 * tr.rtm4) * tr.foeew * a_foeew;
   if (tr.cold) a_t0 += R(0.545) * R(0.17) * a_fwat * (tr.tp1 * (R(2) - tr.tp1));
 
   // ---- latent-heat ratios (AD :988-991)

@@ -23,13 +23,15 @@ CS2_HD void adj_step_fwd_tl(const DevParams<R>& p, R rap, R ap_i, R z3, R z4, R 
   const bool clipped = qs1 > p.ZQMAX;
   const R qsc = clipped ? p.ZQMAX : qs1;
   const R qsc_i = clipped ? R(0) : (rap * foeew_i - ap_i * rap * rap * foeew);
-  const R cor = rcp(R(1) - p.RETV * qsc);
+  const R a = R(1) - p.RETV * qsc;
+  const R cor = rcp(a);
+  const R z2s = z5 * rt * rt;
+  const R a2 = a * a;
+  const R rden = a2 * rcp(a2 + qsc * z2s);  // same statements as adj_step<LIN> (cs2_physics.cuh): bit-identical trajectories
   const R cor_i = p.RETV * qsc_i * cor * cor;
   const R qs = qsc * cor;
   const R qs_i = qsc_i * cor + qsc * cor_i;
-  const R z2s = z5 * rt * rt;
   const R z2s_i = R(-2) * z2s * t_i * rt;
-  const R rden = rcp(R(1) + qs * cor * z2s);
   const R cond = (q - qs) * rden;
   const R cond_i = (q_i - qs_i) * rden - cond * (qs_i * cor * z2s + qs * cor_i * z2s + qs * cor * z2s_i) * rden;
   t += zal * cond;
@@ -86,13 +88,14 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
   const R foeew_i = z3es * (p.RTT - z4es) * t_i * foeew * rtm4 * rtm4;
   const R esdp1 = foeew * rap;
   const bool clip_esdp = esdp1 > p.ZQMAX;
-  const R esdp = clip_esdp ? p.ZQMAX : esdp1;
   const R esdp_i = clip_esdp ? zero : (foeew_i * rap - foeew * d.ap * rap * rap);
   const R facw = p.R5LES * rtw * rtw, faci = p.R5IES * rti * rti;
   const R facw_i = R(-2) * facw * t_i * rtw, faci_i = R(-2) * faci * t_i * rti;
   const R fac = fwat * facw + (one - fwat) * faci;
   const R fac_i = fwat_i * (facw - faci) + fwat * facw_i + (one - fwat) * faci_i;
-  const R cor = rcp(one - p.RETV * esdp);
+  // 1 / (1 - RETV esdp) = ap / (ap - RETV foeew) where the clip does not bind: the reciprocal the subsidence term needs anyway
+  const R fac2 = rcp(in.ap - p.RETV * foeew);
+  const R cor = clip_esdp ? p.cor_clip : in.ap * fac2;
   const R cor_i = p.RETV * esdp_i * cor * cor;
   const R dqsdtemp = fac * cor * in.qsat;
   const R dqsdtemp_i = fac_i * cor * in.qsat + fac * cor_i * in.qsat + fac * cor * d.qsat;
@@ -159,7 +162,6 @@ CS2_HD void level_fwd_tl(const DevParams<R>& p, const LevelIn<R>& in, const Leve
   const R fac1 = rcp(p.RD * t0);
   const R rho = in.ap * fac1;
   const R rho_i = (d.ap - in.ap * t_i * (p.RD * fac1)) * fac1;
-  const R fac2 = rcp(in.ap - p.RETV * foeew);
   const R rodqsdp = -rho * in.qsat * fac2;
   const R rodqsdp_i = (-rho_i * in.qsat - rho * d.qsat + rho * in.qsat * (d.ap - p.RETV * foeew_i) * fac2) * fac2;
   const R ldcp = fwat * lvdcp + (one - fwat) * lsdcp;
