@@ -258,6 +258,10 @@ class _Ranks:
             fn()
         self.barrier()
         a, b = _events()
+        try:  # ~0.2 ms of device-side spinning queued ahead of the start event: the host gets the first calls enqueued while the
+            torch.cuda._sleep(400_000)  # device is still busy, so the timed region holds GPU work only (no launch gap at its head)
+        except Exception:  # pragma: no cover
+            pass
         a.record()
         for _ in range(reps):
             fn()
@@ -529,9 +533,9 @@ def run_gpu_arm(args):
                              p["yrphnc"], gt4py_config=cfg, ad_predicates="tl")
         stest(s, dt, enable_validation=True, verbose=False)
         variants["symmetry_norm3_max_eps"] = stest.norm3_max
-        tl_ms = R.timed(lambda: stest.cloudsc2_tl(s, dt, out_tendencies=stest.tends_tl, out_diagnostics=stest.diags_tl), 10, 3)
-        ad_ms = R.timed(lambda: stest.cloudsc2_ad(s, dt, out_tendencies=stest.tends_ad, out_diagnostics=stest.diags_ad), 10, 3)
-        sat_ms = R.timed(lambda: sat(state, out=diags), 20, 3)
+        tl_ms = R.timed(lambda: stest.cloudsc2_tl(s, dt, out_tendencies=stest.tends_tl, out_diagnostics=stest.diags_tl), 30, 3)
+        ad_ms = R.timed(lambda: stest.cloudsc2_ad(s, dt, out_tendencies=stest.tends_ad, out_diagnostics=stest.diags_ad), 30, 3)
+        sat_ms = R.timed(lambda: sat(state, out=diags), 50, 3)
         kernels += [kernel_entry("tl", "tl_kernel", tl_ms), kernel_entry("ad", "nl_kernel<LIN>+ad_bwd_kernel", ad_ms),
                     kernel_entry("saturation", "saturation_kernel", sat_ms)]
         # the streaming helpers and the reductions of the two harnesses (unfused orchestration), same columns
@@ -574,8 +578,8 @@ def run_gpu_arm(args):
             d32 = sat32(state32)
             state32.update(d32)
             t32, g32 = nl32(state32, dt)
-            nl32_ms = R.timed(lambda: nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32), 20, 3)
-            step32_ms = R.timed(lambda: (sat32(state32, out=d32), nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32)), 20, 3)
+            nl32_ms = R.timed(lambda: nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32), 50, 3)
+            step32_ms = R.timed(lambda: (sat32(state32, out=d32), nl32(state32, dt, out_tendencies=t32, out_diagnostics=g32)), 50, 3)
             k32 = kernel_entry("nl", "nl_kernel", nl32_ms, es=4, dn="f32")
             kernels.append(k32)
             variants["nl_fp32"] = {"ms": nl32_ms, "columns_per_s": k32["columns_per_s"], "achieved_GBs": k32["achieved"],

@@ -11,6 +11,7 @@ fallback -- calling a stencil with host tensors raises `CUDAExtensionError`.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Any, Callable, Dict, Optional, Tuple
 
 import numpy as np
@@ -48,6 +49,9 @@ class StencilObject:
         self._tables_key = None
         self._tables_dev: Optional[torch.Tensor] = None
         self._events = []
+        # validated (layout, device pointer) per tensor OBJECT: id -> (weakref, (nx, nlevs, stride, code, ptr)).  The same
+        # views come back call after call (Field.data hands out one view object per field), so the layout checks run once.
+        self._ptr_cache: Dict[int, Tuple[Any, Tuple[int, int, int, int, int]]] = {}
 
     # ---- helpers -----------------------------------------------------------------------
     @staticmethod
@@ -81,12 +85,22 @@ class StencilObject:
         return _lib.Dims(nx, stride, (nlevs - 1) if nlev is None else nlev, code)
 
     def _ptr(self, arr: torch.Tensor, dims: _lib.Dims, what: str) -> int:
-        nx, nlevs, stride, code = self._layout(arr, what)
+        hit = self._ptr_cache.get(id(arr))
+        if hit is not None and hit[0]() is arr:
+            nx, nlevs, stride, code, ptr = hit[1]
+        else:
+            nx, nlevs, stride, code = self._layout(arr, what)
+            # (torch reports data_ptr() == 0 for views without elements, e.g. an empty column shard)
+            ptr = arr.untyped_storage().data_ptr() + arr.storage_offset() * arr.element_size()
+            if len(self._ptr_cache) >= 1024:  # entries of tensors that no longer exist
+                self._ptr_cache = {k: v for k, v in self._ptr_cache.items() if v[0]() is not None}
+                if len(self._ptr_cache) >= 1024:
+                    self._ptr_cache.clear()
+            self._ptr_cache[id(arr)] = (weakref.ref(arr), (nx, nlevs, stride, code, ptr))
         if nx != dims.ncol or stride != dims.ncol_stride or code != dims.dtype or nlevs != dims.nlev + 1:
             raise ValueError(f"{what}: layout {(nx, nlevs, stride, code)} differs from the call's "
                              f"{(dims.ncol, dims.nlev + 1, dims.ncol_stride, dims.dtype)}")
-        # (torch reports data_ptr() == 0 for views without elements, e.g. an empty column shard)
-        return arr.untyped_storage().data_ptr() + arr.storage_offset() * arr.element_size()
+        return ptr
 
     @staticmethod
     def _stream(ref: torch.Tensor) -> int:
