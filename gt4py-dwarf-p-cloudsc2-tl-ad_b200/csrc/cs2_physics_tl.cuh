@@ -13,27 +13,28 @@
 
 namespace cs2 {
 
-// one Newton step of the saturation adjustment with its tangent (cuadjtqs.py TL :22-55)
+// one Newton step of the saturation adjustment with its tangent (cuadjtqs.py TL :22-55).  The trajectory statements are those of
+// adj_step<LIN> (cs2_physics.cuh), so the TL and AD trajectories stay bit-identical; the tangent applies the step's local
+// Jacobian (adj_step_coef: cond_i = rden q_i + ct t_i + cap ap_i), the very coefficients whose transpose the AD sweep applies.
 template <class R>
 CS2_HD void adj_step_fwd_tl(const DevParams<R>& p, R rap, R ap_i, R z3, R z4, R z5, R zal, R& t, R& q, R& t_i, R& q_i) {
-  const R rt = rcp(t - z4);
-  const R foeew = p.R2ES * exp_(z3 * (t - p.RTT) * rt);
-  const R foeew_i = foeew * z3 * (p.RTT - z4) * t_i * rt * rt;
-  const R qs1 = foeew * rap;
-  const bool clipped = qs1 > p.ZQMAX;
-  const R qsc = clipped ? p.ZQMAX : qs1;
-  const R qsc_i = clipped ? R(0) : (rap * foeew_i - ap_i * rap * rap * foeew);
-  const R a = R(1) - p.RETV * qsc;
-  const R cor = rcp(a);
-  const R z2s = z5 * rt * rt;
+  AdjStep<R> s;
+  s.rt = rcp(t - z4);
+  s.foeew = p.R2ES * exp_(z3 * (t - p.RTT) * s.rt);
+  const R qs1 = s.foeew * rap;
+  s.clipped = qs1 > p.ZQMAX;
+  s.qsc = s.clipped ? p.ZQMAX : qs1;
+  s.z2s = z5 * s.rt * s.rt;
+  const R a = R(1) - p.RETV * s.qsc;
+  s.cor = rcp(a);
   const R a2 = a * a;
-  const R rden = a2 * rcp(a2 + qsc * z2s);  // same statements as adj_step<LIN> (cs2_physics.cuh): bit-identical trajectories
-  const R cor_i = p.RETV * qsc_i * cor * cor;
-  const R qs = qsc * cor;
-  const R qs_i = qsc_i * cor + qsc * cor_i;
-  const R z2s_i = R(-2) * z2s * t_i * rt;
-  const R cond = (q - qs) * rden;
-  const R cond_i = (q_i - qs_i) * rden - cond * (qs_i * cor * z2s + qs * cor_i * z2s + qs * cor * z2s_i) * rden;
+  s.rden = a2 * rcp(a2 + s.qsc * s.z2s);
+  s.qs = s.qsc * s.cor;
+  s.cond = (q - s.qs) * s.rden;
+  R ct, cap;
+  adj_step_coef(p, rap, z3 * (p.RTT - z4), s, ct, cap);
+  const R cond = s.cond;
+  const R cond_i = s.rden * q_i + ct * t_i + cap * ap_i;
   t += zal * cond;
   t_i += zal * cond_i;
   q -= cond;
