@@ -557,8 +557,8 @@ def run_gpu_arm(args):
             ("state_increment", "state_increment_kernel", lambda: stest.state_increment(s, out=stest.state_i)),
             ("perturbed_state", "perturbed_state_kernel", lambda: pert(s, out=state_p)),
             ("taylor_sums", "taylor_partial_kernel", lambda: tsum(tl_f, nl_f, tl_i, tbuf)),  # 30 distinct fields, as in a Taylor run
-            ("symmetry_norm1", "symmetry_norm_kernel", lambda: stest.get_norm1(stest.tends_tl, stest.diags_tl)),
-            ("symmetry_norm2", "symmetry_norm_kernel", lambda: stest.get_norm2(stest.state_i, stest.tends_ad, stest.diags_ad)),
+            ("symmetry_norm1", "symmetry_norm_kernel[norm1]", lambda: stest.get_norm1(stest.tends_tl, stest.diags_tl)),
+            ("symmetry_norm2", "symmetry_norm_kernel[norm2]", lambda: stest.get_norm2(stest.state_i, stest.tends_ad, stest.diags_ad)),
         ):
             kernels.append(kernel_entry(name, kernel, R.timed(fn, 10, 3)))
         del pert, state_p
