@@ -449,6 +449,44 @@ def test_fused_increment_tl_equals_unfused(dtype, ignore_supsat):
                 assert np.abs(b[k].numpy()).max() == 0, k
 
 
+def test_host_side_caches_follow_the_tensors():
+    """Field.data hands out one cached view per buffer and the stencil objects cache the validated pointer per tensor
+    object: fresh output storages on every call (old ones freed, so addresses and Python ids get reused), a replaced buffer
+    and a second grid size through the SAME component must all be followed."""
+    import gc
+
+    g = gh()
+    from cloudsc2_b200 import iox
+    from cloudsc2_b200.physics.common.saturation import Saturation
+    from cloudsc2_b200.physics.nonlinear.microphysics import Cloudsc2NL
+
+    cfg, grid, state = g.make_grid_state("base", np.float64, 100)
+    p = iox.ifs_defaults()
+    state.update(Saturation(grid, 1, True, p["yoethf"], p["yomcst"], gt4py_config=cfg)(state))
+    nl = Cloudsc2NL(grid, True, False, p["yoethf"], p["yomcst"], p["yrecldp"], p["yrephli"], p["yrphnc"], gt4py_config=cfg)
+    dt = timedelta(seconds=H.DT)
+    tn, dg = nl(state, dt)
+    first = {k: v.numpy() for k, v in {**tn, **dg}.items() if hasattr(v, "numpy")}
+    for _ in range(40):  # new output storages each time; the previous ones are garbage
+        tn, dg = nl(state, dt)
+        for k, v in first.items():
+            assert np.array_equal({**tn, **dg}[k].numpy(), v), k
+        del tn, dg
+        gc.collect()
+    # the same Field object with a REPLACED buffer: the cached view must not survive
+    fld = state["f_t"]
+    view = fld.data
+    assert fld.data is view
+    original = fld.buffer
+    fld.buffer = original.clone() + 1.0
+    assert fld.data is not view and fld.data.data_ptr() == fld.buffer.data_ptr()
+    tn, dg = nl(state, dt)
+    assert not np.array_equal(tn["f_t"].numpy(), first["f_t"])  # one kelvin warmer: different tendencies
+    fld.buffer = original
+    tn, dg = nl(state, dt)
+    assert np.array_equal(tn["f_t"].numpy(), first["f_t"])
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("ncol", [100, 777])
 def test_taylor_fused_sums_equal_unfused(dtype, ncol):

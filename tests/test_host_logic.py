@@ -38,6 +38,14 @@ def test_storage_layout_and_logical_view():
     assert float(f.data[7, 0, 3]) == arr[3, 7]
     h = zeros(grid, (I, J, K - 1 / 2), gt4py_config=CPU)
     assert h.data.shape == (100, 1, 138)
+    # one view object per (buffer, nx): handed out again, rebuilt when either changes
+    view = f.data
+    assert f.data is view
+    f.buffer = f.buffer.clone()
+    assert f.data is not view and f.data.data_ptr() == f.buffer.data_ptr()
+    view = f.data
+    f.nx = 64
+    assert f.data is not view and f.data.shape == (64, 1, 138)
     assert grid.grids[I, J, K].shape == (100, 1, 137) and grid.grids[I, J, K - 1 / 2].shape == (100, 1, 138)
 
 
