@@ -757,7 +757,9 @@ cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 namespace {
 // AD workspace: [jsel: int32 per column] [checkpoint planes | overlap-carry plane]; with -DCS2_EXPERIMENTS also [chunk ticket
 // counter] [chunk hand-over slots: 3 values per column and chunk boundary, up to kMaxAdChunks - 1 boundaries]
+#ifdef CS2_EXPERIMENTS
 constexpr int kMaxAdChunks = 8;
+#endif
 struct AdWorkspace {
   size_t off_extra, off_sync, sync_bytes, off_carry, total;
 };
