@@ -255,6 +255,9 @@ taylor_nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __rest
 #ifndef CS2_TL_EVAP_MAXNREG
 #define CS2_TL_EVAP_MAXNREG 168  // the evaporation branch (non-default flags) does not fit 128 registers without spills
 #endif
+#ifndef CS2_AD_MAXNREG_F32
+#define CS2_AD_MAXNREG_F32 128  // fp32 values take one register: the backward sweep fits 128 = 16 warps per SM, every column resident
+#endif
 #ifndef CS2_AD_MAXNREG
 #define CS2_AD_MAXNREG 240
 #endif
@@ -288,7 +291,7 @@ tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
 }
 
 template <class R, int NS, bool EVAP, bool NORM = false>
-__global__ void __maxnreg__(EVAP ? 255 : CS2_AD_MAXNREG)
+__global__ void __maxnreg__(EVAP ? 255 : (sizeof(R) == 4 ? CS2_AD_MAXNREG_F32 : CS2_AD_MAXNREG))
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS + (EVAP ? 2 : 0)> in_s, const int32_t* __restrict__ jsel,
