@@ -253,7 +253,7 @@ taylor_nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __rest
 #define CS2_TL_MAXNREG 128
 #endif
 #ifndef CS2_TL_EVAP_MAXNREG
-#define CS2_TL_EVAP_MAXNREG 168  // the evaporation branch (non-default flags) does not fit 128 registers without spills
+#define CS2_TL_EVAP_MAXNREG 168  // the fp64 evaporation branch (non-default flags) does not fit 128 registers without spills
 #endif
 #ifndef CS2_AD_MAXNREG_F32
 #define CS2_AD_MAXNREG_F32 128  // fp32 values take one register: the backward sweep fits 128 = 16 warps per SM, every column resident
@@ -262,7 +262,7 @@ taylor_nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __rest
 #define CS2_AD_MAXNREG 240
 #endif
 template <class R, bool EVAP>
-__global__ void __maxnreg__(EVAP ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
+__global__ void __maxnreg__((EVAP && sizeof(R) == 8) ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
 tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
           const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
@@ -276,7 +276,7 @@ tl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ 
 
 // fused state_increment + TL (cs2_tl_increment)
 template <class R, bool EVAP, bool NORM>
-__global__ void __maxnreg__(EVAP ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
+__global__ void __maxnreg__((EVAP && sizeof(R) == 8) ? CS2_TL_EVAP_MAXNREG : CS2_TL_MAXNREG)
 tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g,
               const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev, R fac,
@@ -291,7 +291,7 @@ tl_inc_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restric
 }
 
 template <class R, int NS, bool EVAP, bool NORM = false>
-__global__ void __maxnreg__(EVAP ? 255 : (sizeof(R) == 4 ? CS2_AD_MAXNREG_F32 : CS2_AD_MAXNREG))
+__global__ void __maxnreg__(sizeof(R) == 4 ? CS2_AD_MAXNREG_F32 : (EVAP ? 255 : CS2_AD_MAXNREG))
 ad_bwd_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
               const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::ADOut<R> a,
               const __grid_constant__ cs2::Streams<R, NS + (EVAP ? 2 : 0)> in_s, const int32_t* __restrict__ jsel,
