@@ -140,8 +140,14 @@ perturbed_state_kernel(const __grid_constant__ StatePtrs<R> f, R fac, int64_t nc
 
 // CKPT: record the transcendentals (AD forward, checkpoint mode); LIN: AD forward sweep (trajectory evaluated in the
 // same form as the TL / AD-backward kernels evaluate it)
+#ifndef CS2_NLP_MAXNREG
+#define CS2_NLP_MAXNREG 128  // the fused perturbed-NL / Taylor-factor sweeps
+#endif
+#ifndef CS2_NL_MAXNREG
+#define CS2_NL_MAXNREG 96  // spill-free in every instantiation; 20 warps per SM when the grid has them (1 M columns: -5 %)
+#endif
 template <class R, class C, bool CKPT, bool LIN>
-__global__ void __launch_bounds__(kColumnBlock, 7)
+__global__ void __maxnreg__(CS2_NL_MAXNREG)
 nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
           const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::Streams<R, cs2::I_NL> in_s,
           int64_t ncol, int64_t S, int nlev, int ad_ref, int32_t* jsel_out, R* ck, R* cov_out) {
@@ -205,7 +211,7 @@ nl_split_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restr
 #endif  // CS2_EXPERIMENTS
 
 template <class R, class C>
-__global__ void __launch_bounds__(kColumnBlock, 7)
+__global__ void __maxnreg__(CS2_NLP_MAXNREG)
 nlp_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
            const __grid_constant__ cs2::NLFields<R> f, const __grid_constant__ cs2::NLFields<R> g, R fac,
            const __grid_constant__ cs2::Streams<R, 2 * cs2::I_NL> in_s, int64_t ncol, int64_t S, int nlev) {
@@ -222,7 +228,7 @@ __device__ __forceinline__ double warp_sum(double v);
 // One Taylor-test factor in one sweep: NL of x + f2 * (f1 * x) and SUM(F_p - F_nl) per output field (cs2_taylor_nl_sums).
 // Per-CTA partial sums go to `partial[field][blockIdx.x]`; taylor_final_kernel adds them up in a fixed order.
 template <class R, class C>
-__global__ void __launch_bounds__(kColumnBlock, 7)
+__global__ void __maxnreg__(CS2_NLP_MAXNREG)
 taylor_nl_kernel(const __grid_constant__ cs2::DevParams<R> p, const void* __restrict__ tables,
                  const __grid_constant__ cs2::NLFields<R> f, R f1, R f2, int ignore_supsat,
                  const __grid_constant__ cs2::Streams<R, cs2::I_NL + cs2::T_N> in_s, int64_t ncol, int64_t S, int nlev,
