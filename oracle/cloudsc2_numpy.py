@@ -26,7 +26,8 @@ Reference files restated here (relative to /root/reference/src/cloudsc2_gt4py/ph
   tangent_linear/validation.py:219-261        -> taylor_norm
   adjoint/validation.py:167-215               -> symmetry_norms
 
-Parity unpinned against a live reference run (see oracle/__init__.py).
+Parity: pinned to outputs of the reference's own stencil sources executed here by oracle/gtscript_exec.py (bit-identical in
+fp64 on every field of every case, tests/test_ref_exec.py; fixtures tests/golden/ref_*.npz) -- see oracle/__init__.py.
 """
 from __future__ import annotations
 
